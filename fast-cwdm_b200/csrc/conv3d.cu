@@ -1,0 +1,582 @@
+// K5: 3-D convolution (3x3x3 "same" or 1x1x1, stride 1) as a tcgen05 implicit GEMM for sm_100a.
+//
+// Replaces nn.Conv3d -> cuDNN fp32 (guided_diffusion/nn.py:22-32; wunet.py:139,188,213,220,483,704).
+//
+// GEMM view:  M = output voxels, N = C_out, K = k^3 * C_in.  Activations are channels-last bf16
+// (N, D, H, W, C), weights pre-packed [tap][C_out][C_in] bf16, accumulation fp32 in TMEM.
+//
+// One CTA (256 threads, persistent over a static round-robin tile list) owns an output block of
+//   TD (depth) x 16 (H) x 8 (W) voxels  x  N_TILE output channels,
+// i.e. TD accumulators of 128 rows x N_TILE fp32 columns in tensor memory.  Per 64-channel block of C_in:
+//   * the A producer (warp 0, one lane) TMA-loads TD+2 halo planes (18 x 10 voxels x 64 ch = 18x10 rows of
+//     128 B, SWIZZLE_128B, out-of-bounds rows zero-filled by the TMA unit = the conv's zero padding) into a
+//     ring of plane slots with per-slot full/empty mbarriers;
+//   * the B producer (warp 1, one lane) TMA-loads one [N_TILE x 64] weight tile per filter tap into its ring;
+//   * the MMA issuer (warp 2, one lane) walks the 27 taps; for tap (kd,kh,kw) and output plane j the A operand
+//     is the SAME halo plane slot (j+kd) read through a K-major SWIZZLE_128B UMMA descriptor whose start address
+//     is offset by (kh*10 + kw) rows and whose 8-row-group stride (SBO) is the halo row pitch (10 rows): every
+//     activation byte is fetched from L2 once per tile and reused for up to 27 taps x TD planes, and every
+//     weight tile is reused for TD x 128 voxels;  tcgen05.commit releases plane slots / weight stages;
+//   * the epilogue (warps 4-7) drains the accumulators with tcgen05.ld, adds bias (+ per-(n,c) timestep
+//     embedding) (+ residual), converts to bf16 and stores channels-last; a second TMEM accumulator stage lets
+//     it overlap the next tile's MMAs.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace fcwdm {
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trap (CUDA error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("fcwdm conv3d: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+                   threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, M = 128, N from idesc, K = 16.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4, [16,30) LBO >> 4 (unused for swizzled K-major), [32,46) SBO >> 4 = byte stride
+//   between 8-row groups, [46,48) version = 1 (sm_100), [49,52) base offset = 0 (the XOR pattern is a function of
+//   the absolute smem address and all tiles sit in 1024-B aligned slots), [61,64) layout = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------------
+struct ConvArgs {
+    int N, D, H, W;
+    int Cout;        // real output channels (multiple of 8)
+    int n_cb;        // C_in_padded / 64
+    int n_nt, n_wt, n_ht, n_dt;
+    int num_tiles;
+    const float* bias;        // [Cout] or null
+    const float* chan_bias;   // [N][Cout] or null
+    const __nv_bfloat16* residual;
+    long long res_ld;
+    __nv_bfloat16* y;
+    long long y_ld;
+};
+
+template <int N_TILE, int TD, int KS>
+struct ConvCfg {
+    static constexpr int PAD = KS / 2;
+    static constexpr int TAPS = KS * KS * KS;
+    static constexpr int ROWP = 8 + 2 * PAD;             // halo row pitch in voxels (rows of 128 B)
+    static constexpr int HROWS = 16 + 2 * PAD;
+    static constexpr int PLANE_BYTES = HROWS * ROWP * 128;
+    static constexpr int SLOT_BYTES = (PLANE_BYTES + 1023) / 1024 * 1024;
+    static constexpr int PLANES = TD + 2 * PAD;
+    static constexpr int B_BYTES = N_TILE * 128;
+    static constexpr int B_STAGES = (N_TILE >= 128) ? 3 : 4;
+    static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;  // 1 KB alignment slack + 1 KB barriers
+    static constexpr int A_SLOTS_RAW = (SMEM_BUDGET - B_STAGES * B_BYTES) / SLOT_BYTES;
+    static constexpr int A_SLOTS = A_SLOTS_RAW > 12 ? 12 : A_SLOTS_RAW;
+    static constexpr int ACC_COLS = TD * N_TILE;
+    static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
+    static constexpr int TMEM_RAW = ACC_STAGES * ACC_COLS;
+    static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : TMEM_RAW <= 64 ? 64 : TMEM_RAW <= 128 ? 128 : TMEM_RAW <= 256 ? 256 : 512;
+    static constexpr int SMEM_BYTES = 1024 + A_SLOTS * SLOT_BYTES + B_STAGES * B_BYTES + 1024;
+    static constexpr int CHUNK = 16;                     // accumulator columns per tcgen05.ld
+    static_assert(A_SLOTS >= TD + 1, "not enough plane slots");
+    static_assert(ACC_COLS <= 512, "accumulators exceed tensor memory");
+    static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "invalid UMMA N");
+};
+
+struct TileCoord {
+    int n, d0, h0, w0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(int tile, const ConvArgs& a, int td, int n_tile) {
+    TileCoord t;
+    int r = tile;
+    const int nt = r % a.n_nt; r /= a.n_nt;
+    const int wt = r % a.n_wt; r /= a.n_wt;
+    const int ht = r % a.n_ht; r /= a.n_ht;
+    const int dt = r % a.n_dt; r /= a.n_dt;
+    t.n = r;
+    t.d0 = dt * td;
+    t.h0 = ht * 16;
+    t.w0 = wt * 8;
+    t.n0 = nt * n_tile;
+    return t;
+}
+
+template <int N_TILE, int TD, int KS>
+__global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                              const __grid_constant__ CUtensorMap map_b,
+                                                              const ConvArgs args) {
+    using Cfg = ConvCfg<N_TILE, TD, KS>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_b = smem_a + Cfg::A_SLOTS * Cfg::SLOT_BYTES;
+    const uint32_t bars = smem_b + Cfg::B_STAGES * Cfg::B_BYTES;
+    // barrier layout (8 B each)
+    const uint32_t full_a = bars;
+    const uint32_t empty_a = full_a + 8 * Cfg::A_SLOTS;
+    const uint32_t full_b = empty_a + 8 * Cfg::A_SLOTS;
+    const uint32_t empty_b = full_b + 8 * Cfg::B_STAGES;
+    const uint32_t tmem_full = empty_b + 8 * Cfg::B_STAGES;
+    const uint32_t tmem_empty = tmem_full + 8 * Cfg::ACC_STAGES;
+    const uint32_t tmem_slot = tmem_empty + 8 * Cfg::ACC_STAGES;   // 4 B: TMEM base address
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::A_SLOTS; ++i) {
+            mbar_init(full_a + 8 * i, 1);
+            mbar_init(empty_a + 8 * i, 1);
+        }
+        for (int i = 0; i < Cfg::B_STAGES; ++i) {
+            mbar_init(full_b + 8 * i, 1);
+            mbar_init(empty_b + 8 * i, 1);
+        }
+        for (int i = 0; i < Cfg::ACC_STAGES; ++i) {
+            mbar_init(tmem_full + 8 * i, 1);
+            mbar_init(tmem_empty + 8 * i, 4);
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 3) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ================================ A producer: halo planes ================================
+        if (lane == 0) {
+            uint32_t q = 0;
+            for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+                const TileCoord tc = decode_tile(tile, args, TD, N_TILE);
+                for (int cb = 0; cb < args.n_cb; ++cb) {
+                    for (int p = 0; p < Cfg::PLANES; ++p, ++q) {
+                        const uint32_t slot = q % Cfg::A_SLOTS, ph = (q / Cfg::A_SLOTS) & 1;
+                        mbar_wait(empty_a + 8 * slot, ph ^ 1);
+                        mbar_arrive_expect_tx(full_a + 8 * slot, Cfg::PLANE_BYTES);
+                        tma_load_5d(smem_a + slot * Cfg::SLOT_BYTES, &map_a, full_a + 8 * slot, cb * 64,
+                                    tc.w0 - Cfg::PAD, tc.h0 - Cfg::PAD, tc.d0 + p - Cfg::PAD, tc.n);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ B producer: weight tiles ================================
+        if (lane == 0) {
+            uint32_t r = 0;
+            for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+                const TileCoord tc = decode_tile(tile, args, TD, N_TILE);
+                for (int cb = 0; cb < args.n_cb; ++cb) {
+                    for (int tap = 0; tap < Cfg::TAPS; ++tap, ++r) {
+                        const uint32_t st = r % Cfg::B_STAGES, ph = (r / Cfg::B_STAGES) & 1;
+                        mbar_wait(empty_b + 8 * st, ph ^ 1);
+                        mbar_arrive_expect_tx(full_b + 8 * st, Cfg::B_BYTES);
+                        tma_load_3d(smem_b + st * Cfg::B_BYTES, &map_b, full_b + 8 * st, cb * 64, tc.n0, tap);
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+            // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) |
+                                       ((uint32_t)(128 >> 4) << 24);
+            uint32_t q_base = 0, r = 0, acc_it = 0;
+            for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++acc_it) {
+                const uint32_t as = acc_it % Cfg::ACC_STAGES, aph = (acc_it / Cfg::ACC_STAGES) & 1;
+                mbar_wait(tmem_empty + 8 * as, aph ^ 1);
+                tc_fence_after();
+                const uint32_t acc0 = tmem_base + as * Cfg::ACC_COLS;
+                for (int cb = 0; cb < args.n_cb; ++cb) {
+                    int planes_ready = 0;
+                    for (int kd = 0; kd < KS; ++kd) {
+                        while (planes_ready < kd + TD) {
+                            const uint32_t qq = q_base + planes_ready;
+                            mbar_wait(full_a + 8 * (qq % Cfg::A_SLOTS), (qq / Cfg::A_SLOTS) & 1);
+                            ++planes_ready;
+                        }
+                        tc_fence_after();
+                        for (int kh = 0; kh < KS; ++kh) {
+                            for (int kw = 0; kw < KS; ++kw, ++r) {
+                                const uint32_t st = r % Cfg::B_STAGES;
+                                mbar_wait(full_b + 8 * st, (r / Cfg::B_STAGES) & 1);
+                                tc_fence_after();
+                                const uint32_t b_addr = smem_b + st * Cfg::B_BYTES;
+                                const bool first_tap = (cb == 0) && (kd == 0) && (kh == 0) && (kw == 0);
+#pragma unroll
+                                for (int j = 0; j < TD; ++j) {
+                                    const uint32_t qq = q_base + kd + j;
+                                    const uint32_t a_addr = smem_a + (qq % Cfg::A_SLOTS) * Cfg::SLOT_BYTES +
+                                                            (kh * Cfg::ROWP + kw) * 128;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        umma_bf16(acc0 + j * N_TILE, make_sw128_desc(a_addr + k * 32, Cfg::ROWP * 128),
+                                                  make_sw128_desc(b_addr + k * 32, 1024), idesc,
+                                                  (first_tap && k == 0) ? 0u : 1u);
+                                    }
+                                }
+                                umma_commit(empty_b + 8 * st);   // weight stage free once these MMAs retire
+                            }
+                        }
+                        // plane kd is not needed by later taps of this channel block
+                        umma_commit(empty_a + 8 * ((q_base + kd) % Cfg::A_SLOTS));
+                    }
+                    for (int p = KS; p < Cfg::PLANES; ++p) umma_commit(empty_a + 8 * ((q_base + p) % Cfg::A_SLOTS));
+                    q_base += Cfg::PLANES;
+                }
+                umma_commit(tmem_full + 8 * as);                 // accumulators complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue ================================
+        const int ew = warp - 4;                  // == warp % 4: TMEM lane quarter this warp may access
+        const int row = ew * 32 + lane;           // accumulator row = voxel within the 16 x 8 tile
+        const int hh = row >> 3, ww = row & 7;
+        uint32_t acc_it = 0;
+        for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++acc_it) {
+            const TileCoord tc = decode_tile(tile, args, TD, N_TILE);
+            const uint32_t as = acc_it % Cfg::ACC_STAGES, aph = (acc_it / Cfg::ACC_STAGES) & 1;
+            mbar_wait(tmem_full + 8 * as, aph);
+            tc_fence_after();
+            const int h = tc.h0 + hh, w = tc.w0 + ww;
+            const bool hw_ok = (h < args.H) && (w < args.W);
+#pragma unroll 1
+            for (int j = 0; j < TD; ++j) {
+                const int d = tc.d0 + j;
+                const bool ok = hw_ok && (d < args.D);
+                const long long vox = (((long long)tc.n * args.D + d) * args.H + h) * args.W + w;
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * Cfg::ACC_COLS + j * N_TILE;
+#pragma unroll 1
+                for (int c0 = 0; c0 < N_TILE; c0 += Cfg::CHUNK) {
+                    uint32_t acc[16];
+                    tmem_ld_x16(taddr + c0, acc);
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            const int co = tc.n0 + c0 + g * 8;
+                            if (co < args.Cout) {
+                                float v[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[g * 8 + e]);
+                                if (args.bias != nullptr) {
+                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + co));
+                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + co + 4));
+                                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                                }
+                                if (args.chan_bias != nullptr) {
+                                    const float* cbp = args.chan_bias + (long long)tc.n * args.Cout + co;
+                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(cbp));
+                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(cbp + 4));
+                                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                                }
+                                if (args.residual != nullptr) {
+                                    float rr[8];
+                                    unpack8(*reinterpret_cast<const uint4*>(args.residual + vox * args.res_ld + co), rr);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) v[e] += rr[e];
+                                }
+                                *reinterpret_cast<uint4*>(args.y + vox * args.y_ld + co) = pack8(v);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * as);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// weights (Cout, Cin, k, k, k) f32 -> [tap][Cout_p][Cin_p] bf16, zero padded
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
+                                                           int Cout, int Cin, int Cout_p, int Cin_p, int taps) {
+    const long long total = (long long)taps * Cout_p * Cin_p;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ci = (int)(idx % Cin_p);
+    long long r = idx / Cin_p;
+    const int co = (int)(r % Cout_p);
+    const int tap = (int)(r / Cout_p);
+    float v = 0.f;
+    if (co < Cout && ci < Cin) v = w[((long long)co * Cin + ci) * taps + tap];
+    wp[idx] = __float2bfloat16_rn(v);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+template <int N_TILE, int TD, int KS>
+static cudaError_t set_attr() {
+    return cudaFuncSetAttribute(conv3d_igemm_kernel<N_TILE, TD, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ConvCfg<N_TILE, TD, KS>::SMEM_BYTES);
+}
+
+int conv3d_init_device() {
+    if (g_encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        FCWDM_REQUIRE(e == cudaSuccess && fn != nullptr && qres == cudaDriverEntryPointSuccess, FCWDM_ERR_CUDA,
+                      "fcwdm_init: cuTensorMapEncodeTiled entry point not available (%s)", cudaGetErrorString(e));
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    cudaError_t e = cudaSuccess;
+#define FCWDM_SET(NT, TDV, KSV) \
+    if (e == cudaSuccess) e = set_attr<NT, TDV, KSV>();
+    FCWDM_SET(64, 4, 3) FCWDM_SET(64, 2, 3) FCWDM_SET(64, 1, 3) FCWDM_SET(128, 2, 3) FCWDM_SET(128, 1, 3)
+    FCWDM_SET(16, 4, 3) FCWDM_SET(16, 1, 3) FCWDM_SET(64, 1, 1) FCWDM_SET(128, 1, 1)
+#undef FCWDM_SET
+    FCWDM_REQUIRE(e == cudaSuccess, FCWDM_ERR_CUDA, "fcwdm_init: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    return FCWDM_OK;
+}
+
+template <int N_TILE, int TD, int KS>
+static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, ConvArgs a, cudaStream_t st) {
+    using Cfg = ConvCfg<N_TILE, TD, KS>;
+    a.n_nt = (((a.Cout + 15) / 16 * 16) + N_TILE - 1) / N_TILE;
+    a.n_wt = (a.W + 7) / 8;
+    a.n_ht = (a.H + 15) / 16;
+    a.n_dt = (a.D + TD - 1) / TD;
+    const long long tiles = (long long)a.N * a.n_dt * a.n_ht * a.n_wt * a.n_nt;
+    FCWDM_REQUIRE(tiles < (1ll << 31), FCWDM_ERR_UNSUPPORTED, "fcwdm_conv3d_fwd: too many tiles");
+    a.num_tiles = (int)tiles;
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    conv3d_igemm_kernel<N_TILE, TD, KS><<<grid, 256, Cfg::SMEM_BYTES, st>>>(ma, mb, a);
+    FCWDM_CHECK_LAUNCH("fcwdm_conv3d_fwd");
+    return FCWDM_OK;
+}
+
+static inline long long tiles_for(long long N, long long D, long long H, long long W, long long cout_p, int nt, int td) {
+    return N * ((D + td - 1) / td) * ((H + 15) / 16) * ((W + 7) / 8) * ((cout_p + nt - 1) / nt);
+}
+
+}  // namespace fcwdm
+
+using namespace fcwdm;
+
+extern "C" int64_t fcwdm_conv3d_packed_elems(int64_t Cout, int64_t Cin, int ksize) {
+    if (Cout <= 0 || Cin <= 0 || (ksize != 1 && ksize != 3)) return -1;
+    const int64_t cout_p = (Cout + 15) / 16 * 16, cin_p = (Cin + 63) / 64 * 64;
+    return (int64_t)ksize * ksize * ksize * cout_p * cin_p;
+}
+
+extern "C" int fcwdm_conv3d_pack_weights(const float* w, void* wp, int64_t Cout, int64_t Cin, int ksize, void* stream) {
+    FCWDM_REQUIRE(w && wp, FCWDM_ERR_INVALID, "fcwdm_conv3d_pack_weights: null pointer");
+    FCWDM_REQUIRE(Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3), FCWDM_ERR_INVALID,
+                  "fcwdm_conv3d_pack_weights: bad argument");
+    const int taps = ksize * ksize * ksize;
+    const int cout_p = (int)((Cout + 15) / 16 * 16), cin_p = (int)((Cin + 63) / 64 * 64);
+    const long long total = (long long)taps * cout_p * cin_p;
+    pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        w, (__nv_bfloat16*)wp, (int)Cout, (int)Cin, cout_p, cin_p, taps);
+    FCWDM_CHECK_LAUNCH("fcwdm_conv3d_pack_weights");
+    return FCWDM_OK;
+}
+
+extern "C" int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, const float* bias, const float* chan_bias,
+                                const void* residual, int64_t res_ld, void* y, int64_t y_ld, int64_t N, int64_t D,
+                                int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize, void* stream) {
+    FCWDM_REQUIRE(x && wp && y, FCWDM_ERR_INVALID, "fcwdm_conv3d_fwd: null pointer");
+    FCWDM_REQUIRE(N >= 0 && D >= 0 && H >= 0 && W >= 0 && Cin > 0 && Cout > 0, FCWDM_ERR_INVALID,
+                  "fcwdm_conv3d_fwd: bad dimension");
+    FCWDM_REQUIRE(ksize == 1 || ksize == 3, FCWDM_ERR_UNSUPPORTED, "fcwdm_conv3d_fwd: kernel size %d (only 1, 3)", ksize);
+    FCWDM_REQUIRE(Cout % 8 == 0, FCWDM_ERR_UNSUPPORTED, "fcwdm_conv3d_fwd: C_out must be a multiple of 8");
+    const int64_t cin_p = (Cin + 63) / 64 * 64, cout_p = (Cout + 15) / 16 * 16;
+    FCWDM_REQUIRE(x_ld >= cin_p && x_ld % 8 == 0, FCWDM_ERR_INVALID,
+                  "fcwdm_conv3d_fwd: x_ld (%lld) must be >= C_in rounded up to 64 (%lld) and a multiple of 8",
+                  (long long)x_ld, (long long)cin_p);
+    FCWDM_REQUIRE(y_ld >= Cout && y_ld % 8 == 0 && (residual == nullptr || (res_ld >= Cout && res_ld % 8 == 0)),
+                  FCWDM_ERR_INVALID, "fcwdm_conv3d_fwd: bad y_ld / res_ld");
+    FCWDM_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)wp % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
+                      ((uintptr_t)residual % 16 == 0) && ((uintptr_t)bias % 16 == 0) && ((uintptr_t)chan_bias % 16 == 0),
+                  FCWDM_ERR_INVALID, "fcwdm_conv3d_fwd: pointers must be 16-byte aligned");
+    FCWDM_REQUIRE(D < 32768 && H < 32768 && W < 32768 && N < 32768, FCWDM_ERR_UNSUPPORTED, "fcwdm_conv3d_fwd: dim too large");
+    if (N * D * H * W == 0) return FCWDM_OK;
+    if (g_encode == nullptr) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        int rc = fcwdm_init(dev);
+        if (rc) return rc;
+    }
+    const int pad = ksize / 2;
+    CUtensorMap ma, mb;
+    {
+        cuuint64_t dims[5] = {(cuuint64_t)cin_p, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+        cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2,
+                                 (cuuint64_t)D * H * W * x_ld * 2};
+        cuuint32_t box[5] = {64, (cuuint32_t)(8 + 2 * pad), (cuuint32_t)(16 + 2 * pad), 1, 1};
+        cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        CUresult r = g_encode(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        FCWDM_REQUIRE(r == CUDA_SUCCESS, FCWDM_ERR_CUDA, "fcwdm_conv3d_fwd: activation tensor map encode failed (%d)", (int)r);
+    }
+    const int taps = ksize * ksize * ksize;
+    auto encode_b = [&](int n_tile) -> int {
+        cuuint64_t dims[3] = {(cuuint64_t)cin_p, (cuuint64_t)cout_p, (cuuint64_t)taps};
+        cuuint64_t strides[2] = {(cuuint64_t)cin_p * 2, (cuuint64_t)cout_p * cin_p * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)n_tile, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = g_encode(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wp), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        FCWDM_REQUIRE(r == CUDA_SUCCESS, FCWDM_ERR_CUDA, "fcwdm_conv3d_fwd: weight tensor map encode failed (%d)", (int)r);
+        return FCWDM_OK;
+    };
+    ConvArgs a;
+    a.N = (int)N; a.D = (int)D; a.H = (int)H; a.W = (int)W;
+    a.Cout = (int)Cout;
+    a.n_cb = (int)(cin_p / 64);
+    a.bias = bias; a.chan_bias = chan_bias;
+    a.residual = (const __nv_bfloat16*)residual; a.res_ld = res_ld;
+    a.y = (__nv_bfloat16*)y; a.y_ld = y_ld;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    // tile-shape choice: prefer deep (TD) and wide (N_TILE) tiles for operand reuse, unless that leaves SMs idle
+    const int sms = num_sms();
+    auto util = [&](int nt, int td) {
+        const long long t = tiles_for(N, D, H, W, cout_p, nt, td);
+        const long long waves = (t + sms - 1) / sms;
+        return (double)t / (double)(waves * sms);
+    };
+    int rc;
+    if (ksize == 1) {
+        const int nt = (cout_p % 128 == 0) ? 128 : 64;
+        if ((rc = encode_b(nt))) return rc;
+        return nt == 128 ? launch_conv<128, 1, 1>(ma, mb, a, st) : launch_conv<64, 1, 1>(ma, mb, a, st);
+    }
+    if (cout_p <= 16) {
+        if ((rc = encode_b(16))) return rc;
+        return util(16, 4) >= 0.6 ? launch_conv<16, 4, 3>(ma, mb, a, st) : launch_conv<16, 1, 3>(ma, mb, a, st);
+    }
+    struct Cand { int nt, td; double w; };
+    const Cand cands[5] = {{128, 2, 1.00}, {64, 4, 0.97}, {64, 2, 0.85}, {128, 1, 0.80}, {64, 1, 0.70}};
+    int best = -1;
+    double best_score = -1.0;
+    for (int i = 0; i < 5; ++i) {
+        if (cands[i].nt == 128 && (cout_p % 128 != 0)) continue;
+        const double s = util(cands[i].nt, cands[i].td) * cands[i].w;
+        if (s > best_score) { best_score = s; best = i; }
+    }
+    const int nt = cands[best].nt, td = cands[best].td;
+    if ((rc = encode_b(nt))) return rc;
+    if (nt == 128) return td == 2 ? launch_conv<128, 2, 3>(ma, mb, a, st) : launch_conv<128, 1, 3>(ma, mb, a, st);
+    return td == 4 ? launch_conv<64, 4, 3>(ma, mb, a, st)
+                   : (td == 2 ? launch_conv<64, 2, 3>(ma, mb, a, st) : launch_conv<64, 1, 3>(ma, mb, a, st));
+}

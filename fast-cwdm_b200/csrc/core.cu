@@ -1,0 +1,37 @@
+// Library plumbing for the C-ABI: version, thread-local error text, per-device init.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace fcwdm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int conv3d_init_device();  // conv3d.cu
+
+}  // namespace fcwdm
+
+extern "C" int fcwdm_version(void) { return FCWDM_VERSION; }
+
+extern "C" const char* fcwdm_last_error(void) { return fcwdm::g_err; }
+
+extern "C" int fcwdm_init(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    FCWDM_REQUIRE(e == cudaSuccess, FCWDM_ERR_CUDA, "fcwdm_init: cudaSetDevice(%d) failed: %s", device,
+                  cudaGetErrorString(e));
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+    FCWDM_REQUIRE(major == 10, FCWDM_ERR_ARCH,
+                  "fcwdm_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, major,
+                  minor);
+    return fcwdm::conv3d_init_device();
+}

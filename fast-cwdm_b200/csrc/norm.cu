@@ -1,0 +1,153 @@
+// K4: GroupNorm32 (+SiLU) on channels-last bf16 activations, fp32 math (guided_diffusion/nn.py:17-19).
+//
+// Two HBM-bound passes: `stats` reads x once (per-thread fp32 partial sums -> shared-memory atomics ->
+// one fp64 atomicAdd per (block, group)), `apply` reads x once and writes y once with the affine
+// transform and SiLU fused.  A group at full latent resolution is 2 channels x 1,003,520 voxels, far
+// larger than shared memory, hence the split.
+#include "common.cuh"
+
+namespace fcwdm {
+
+constexpr int kNormThreads = 256;
+
+__global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld,
+                                                                double* __restrict__ stats, int64_t S, int C, int G) {
+    extern __shared__ float sm[];  // [2][C]: per-channel sum, sum of squares
+    const int C8 = C >> 3;
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < 2 * C; i += kNormThreads) sm[i] = 0.f;
+    __syncthreads();
+    const int chunk = threadIdx.x % C8;
+    const int lane = threadIdx.x / C8;
+    const int vpb = kNormThreads / C8;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const __nv_bfloat16* base = x + (int64_t)n * S * ld + chunk * 8;
+    for (int64_t v = (int64_t)blockIdx.x * vpb + lane; v < S; v += (int64_t)gridDim.x * vpb) {
+        float f[8];
+        unpack8(ld_stream_u4(base + v * ld), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s[j] += f[j];
+            q[j] = fmaf(f[j], f[j], q[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sm[chunk * 8 + j], s[j]);
+        atomicAdd(&sm[C + chunk * 8 + j], q[j]);
+    }
+    __syncthreads();
+    const int cpg = C / G;
+    for (int g = threadIdx.x; g < G; g += kNormThreads) {
+        double a = 0.0, b = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            a += (double)sm[c];
+            b += (double)sm[C + c];
+        }
+        atomicAdd(&stats[((int64_t)n * G + g) * 2 + 0], a);
+        atomicAdd(&stats[((int64_t)n * G + g) * 2 + 1], b);
+    }
+}
+
+template <bool kSilu>
+__global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld,
+                                                                __nv_bfloat16* __restrict__ y, int64_t y_ld,
+                                                                const double* __restrict__ stats,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, int64_t S, int C, int G,
+                                                                float eps) {
+    extern __shared__ float sm[];  // [2][C]: scale, shift
+    const int n = blockIdx.y;
+    const int cpg = C / G;
+    const double cnt = (double)S * (double)cpg;
+    for (int c = threadIdx.x; c < C; c += kNormThreads) {
+        const int g = c / cpg;
+        const double mean = stats[((int64_t)n * G + g) * 2 + 0] / cnt;
+        double var = stats[((int64_t)n * G + g) * 2 + 1] / cnt - mean * mean;  // biased variance, as nn.GroupNorm
+        var = var < 0.0 ? 0.0 : var;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float sc = rstd * gamma[c];
+        sm[c] = sc;
+        sm[C + c] = beta[c] - (float)mean * sc;
+    }
+    __syncthreads();
+    const int C8 = C >> 3;
+    const int64_t total = S * C8;
+    const __nv_bfloat16* xb = x + (int64_t)n * S * x_ld;
+    __nv_bfloat16* yb = y + (int64_t)n * S * y_ld;
+    for (int64_t i = (int64_t)blockIdx.x * kNormThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kNormThreads) {
+        const int64_t v = i / C8;
+        const int chunk = (int)(i % C8);
+        float f[8];
+        unpack8(ld_stream_u4(xb + v * x_ld + chunk * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = fmaf(f[j], sm[chunk * 8 + j], sm[C + chunk * 8 + j]);
+            f[j] = kSilu ? silu_f(t) : t;
+        }
+        *reinterpret_cast<uint4*>(yb + v * y_ld + chunk * 8) = pack8(f);
+    }
+}
+
+}  // namespace fcwdm
+
+using namespace fcwdm;
+
+static int gn_check(const char* fn, int64_t N, int64_t S, int64_t C, int64_t G) {
+    FCWDM_REQUIRE(N >= 0 && S >= 0 && C > 0 && G > 0 && N <= 65535, FCWDM_ERR_INVALID, "%s: bad dimension", fn);
+    FCWDM_REQUIRE(C % G == 0, FCWDM_ERR_INVALID, "%s: C (%lld) not divisible by G (%lld)", fn, (long long)C, (long long)G);
+    FCWDM_REQUIRE(C % 8 == 0 && (kNormThreads % (C / 8)) == 0 && C <= 2048, FCWDM_ERR_UNSUPPORTED,
+                  "%s: C must be 8 * a divisor of %d (got %lld)", fn, kNormThreads, (long long)C);
+    return FCWDM_OK;
+}
+
+extern "C" int fcwdm_groupnorm_stats(const void* x, int64_t ld, double* stats, int64_t N, int64_t S, int64_t C,
+                                     int64_t G, void* stream) {
+    FCWDM_REQUIRE(x && stats, FCWDM_ERR_INVALID, "fcwdm_groupnorm_stats: null pointer");
+    int rc = gn_check("fcwdm_groupnorm_stats", N, S, C, G);
+    if (rc) return rc;
+    FCWDM_REQUIRE(ld >= C && ld % 8 == 0, FCWDM_ERR_INVALID, "fcwdm_groupnorm_stats: bad ld");
+    if (N == 0) return FCWDM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N * G, st);
+    FCWDM_REQUIRE(e == cudaSuccess, FCWDM_ERR_CUDA, "fcwdm_groupnorm_stats: memset failed (%s)", cudaGetErrorString(e));
+    if (S == 0) return FCWDM_OK;
+    const int64_t vpb = kNormThreads / (C / 8);
+    int64_t blocks = (S + vpb * 4 - 1) / (vpb * 4);  // >= 4 voxels per thread
+    const int64_t cap = (int64_t)num_sms() * 8 / (N > 8 ? 8 : N);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    dim3 grid((unsigned)blocks, (unsigned)N);
+    gn_stats_kernel<<<grid, kNormThreads, 2 * C * sizeof(float), st>>>((const __nv_bfloat16*)x, ld, stats, S, (int)C,
+                                                                        (int)G);
+    FCWDM_CHECK_LAUNCH("fcwdm_groupnorm_stats");
+    return FCWDM_OK;
+}
+
+extern "C" int fcwdm_groupnorm_apply(const void* x, int64_t x_ld, void* y, int64_t y_ld, const double* stats,
+                                     const float* gamma, const float* beta, int64_t N, int64_t S, int64_t C, int64_t G,
+                                     float eps, int silu, void* stream) {
+    FCWDM_REQUIRE(x && y && stats && gamma && beta, FCWDM_ERR_INVALID, "fcwdm_groupnorm_apply: null pointer");
+    int rc = gn_check("fcwdm_groupnorm_apply", N, S, C, G);
+    if (rc) return rc;
+    FCWDM_REQUIRE(x_ld >= C && y_ld >= C && x_ld % 8 == 0 && y_ld % 8 == 0, FCWDM_ERR_INVALID,
+                  "fcwdm_groupnorm_apply: bad ld");
+    if (N * S == 0) return FCWDM_OK;
+    const int64_t total = S * (C / 8);
+    int64_t blocks = (total + kNormThreads * 4 - 1) / (kNormThreads * 4);
+    const int64_t cap = (int64_t)num_sms() * 8 / (N > 8 ? 8 : N);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    dim3 grid((unsigned)blocks, (unsigned)N);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (silu)
+        gn_apply_kernel<true><<<grid, kNormThreads, 2 * C * sizeof(float), st>>>(
+            (const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)y, y_ld, stats, gamma, beta, S, (int)C, (int)G, eps);
+    else
+        gn_apply_kernel<false><<<grid, kNormThreads, 2 * C * sizeof(float), st>>>(
+            (const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)y, y_ld, stats, gamma, beta, S, (int)C, (int)G, eps);
+    FCWDM_CHECK_LAUNCH("fcwdm_groupnorm_apply");
+    return FCWDM_OK;
+}

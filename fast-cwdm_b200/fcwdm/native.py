@@ -1,0 +1,93 @@
+"""ctypes binding of libfcwdm.so (C-ABI declared in include/fcwdm.h).
+
+This is the thin stub a maintainer of the reference would add: the reference is pure
+Python/PyTorch and has no FFI of its own, so the binding is new.  There is NO CPU or PyTorch fallback: if the
+shared library is missing or the device is not a B200, importing / calling raises.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfcwdm.so")
+
+_c_i64 = ctypes.c_int64
+_c_p = ctypes.c_void_p
+_c_f = ctypes.c_float
+_c_int = ctypes.c_int
+
+# name -> (restype, argtypes); mirrors include/fcwdm.h one to one
+PROTOTYPES = {
+    "fcwdm_version": (_c_int, []),
+    "fcwdm_last_error": (ctypes.c_char_p, []),
+    "fcwdm_init": (_c_int, [_c_int]),
+    "fcwdm_dwt3d_fwd": (_c_int, [_c_p, _c_p, _c_int] + [_c_i64] * 10 + [_c_f, _c_p]),
+    "fcwdm_idwt3d_fwd": (_c_int, [_c_p, _c_p, _c_int] + [_c_i64] * 10 + [_c_f, _c_p]),
+    "fcwdm_dwt3d_cl": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_p] + [_c_i64] * 5 + [_c_f, _c_f, _c_p]),
+    "fcwdm_idwt3d_cl": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_p, _c_i64, _c_p] + [_c_i64] * 5 + [_c_f, _c_p]),
+    "fcwdm_p_sample_step": (_c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_p] + [_c_i64] * 5
+                            + [_c_int, _c_int, _c_p]),
+    "fcwdm_q_sample": (_c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_p]),
+    "fcwdm_sample_to_image": (_c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_p]),
+    "fcwdm_planar_to_cl": (_c_int, [_c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_p]),
+    "fcwdm_cl_to_planar": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_i64, _c_p]),
+    "fcwdm_groupnorm_stats": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_p]),
+    "fcwdm_groupnorm_apply": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64,
+                                       _c_f, _c_int, _c_p]),
+    "fcwdm_timestep_embedding": (_c_int, [_c_p, _c_p, _c_i64, _c_i64, _c_f, _c_p]),
+    "fcwdm_linear": (_c_int, [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_p]),
+    "fcwdm_conv3d_packed_elems": (_c_i64, [_c_i64, _c_i64, _c_int]),
+    "fcwdm_conv3d_pack_weights": (_c_int, [_c_p, _c_p, _c_i64, _c_i64, _c_int, _c_p]),
+    "fcwdm_conv3d_fwd": (_c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64] + [_c_i64] * 6
+                         + [_c_int, _c_p]),
+}
+
+FCWDM_F32, FCWDM_BF16 = 0, 1
+
+_lib = None
+_lock = threading.Lock()
+_inited_devices = set()
+launch_count = 0   # number of C-ABI kernel-launching calls made (bench.py reports it as gpu_launches)
+
+
+class FcwdmError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (no device needed) and attach prototypes."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise FcwdmError(
+                    f"{LIB_PATH} is missing: build it with `python fast-cwdm_b200/fcwdm/build.py` "
+                    "(there is no CPU / PyTorch fallback for the fcwdm hot path)")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in PROTOTYPES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def init(device_index):
+    lib = load()
+    if device_index not in _inited_devices:
+        rc = lib.fcwdm_init(int(device_index))
+        if rc != 0:
+            raise FcwdmError(f"fcwdm_init({device_index}) failed [{rc}]: {lib.fcwdm_last_error().decode()}")
+        _inited_devices.add(device_index)
+    return lib
+
+
+def call(name, *args):
+    """Invoke a status-returning entry point; raise FcwdmError with the library's message on failure."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise FcwdmError(f"{name} failed [{rc}]: {lib.fcwdm_last_error().decode()}")
+    launch_count += 1
+    return rc

@@ -1,0 +1,268 @@
+"""Torch-tensor wrappers over the C-ABI (fcwdm/native.py).  PyTorch is plumbing here: it owns device memory
+and streams; every computation below is a hand-written sm_100a kernel in libfcwdm.so.  CPU tensors are
+rejected -- there is no fallback path."""
+import ctypes
+
+import torch
+
+from . import native
+from .native import FcwdmError
+
+_VP = ctypes.c_void_p
+
+
+def _ptr(t):
+    return _VP(t.data_ptr()) if t is not None else _VP(None)
+
+
+def _stream(dev):
+    return _VP(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _need_cuda(t, what):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{what}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise FcwdmError(f"{what}: tensor is on {t.device}; the fcwdm operators run on CUDA (sm_100a) only and "
+                         "have no CPU fallback")
+
+
+class _on:
+    """Make `dev` current for the launch (the reference's .cuda() used the *current* device,
+    DWT_IDWT_layer.py:505-511; here the input's device decides) and make sure the library is initialised."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.guard = torch.cuda.device(dev)
+
+    def __enter__(self):
+        self.guard.__enter__()
+        native.init(self.dev.index if self.dev.index is not None else torch.cuda.current_device())
+        return _stream(self.dev)
+
+    def __exit__(self, *a):
+        return self.guard.__exit__(*a)
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float32:
+        return native.FCWDM_F32
+    if t.dtype == torch.bfloat16:
+        return native.FCWDM_BF16
+    # the reference's matmul against fp32 band matrices raises "expected scalar type Float" for anything else
+    raise TypeError(f"DWT/IDWT: unsupported dtype {t.dtype} (float32 and bfloat16 are implemented)")
+
+
+def _spatial_contig(x):
+    """Return x with (D,H,W) contiguous, keeping arbitrary N/C strides when possible."""
+    _, _, D, H, W = x.shape
+    if x.stride(4) == 1 and x.stride(3) == W and x.stride(2) == H * W:
+        return x
+    return x.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------
+# planar DWT / IDWT
+# ----------------------------------------------------------------------------------------------------
+def dwt3d_planar(x, lll_scale=1.0, concat=False):
+    """x (N,C,D,H,W) -> 8 bands.  concat=False: tensor (8,N,C,d,h,w); concat=True: (N,8*C,d,h,w) laid out as
+    th.cat([LLL*lll_scale, LLH, ...], dim=1)."""
+    _need_cuda(x, "DWT_3D")
+    if x.dim() != 5:
+        raise AssertionError("DWT_3D expects a 5-D (N, C, D, H, W) input")   # DWT_IDWT_layer.py:525
+    x = _spatial_contig(x)
+    N, C, D, H, W = x.shape
+    if D % 2 or H % 2 or W % 2:
+        raise FcwdmError(f"DWT_3D: D, H, W must be even, got {(D, H, W)}")
+    d, h, w = D // 2, H // 2, W // 2
+    s = d * h * w
+    if concat:
+        out = torch.empty((N, 8 * C, d, h, w), dtype=x.dtype, device=x.device)
+        o_sn, o_sc, o_sb = 8 * C * s, s, C * s
+    else:
+        out = torch.empty((8, N, C, d, h, w), dtype=x.dtype, device=x.device)
+        o_sn, o_sc, o_sb = C * s, s, N * C * s
+    with _on(x.device) as st:
+        native.call("fcwdm_dwt3d_fwd", _ptr(x), _ptr(out), _dtype_code(x), N, C, D, H, W, x.stride(0), x.stride(1),
+                    o_sn, o_sc, o_sb, float(lll_scale), st)
+    return out
+
+
+def idwt3d_planar(bands, lll_scale=1.0, concat=False):
+    """Inverse of dwt3d_planar.  bands: (8,N,C,d,h,w) or, with concat=True, (N,8*C,d,h,w)."""
+    _need_cuda(bands, "IDWT_3D")
+    bands = bands.contiguous()
+    if concat:
+        N, C8, d, h, w = bands.shape
+        C = C8 // 8
+        s = d * h * w
+        b_sn, b_sc, b_sb = 8 * C * s, s, C * s
+    else:
+        _, N, C, d, h, w = bands.shape
+        s = d * h * w
+        b_sn, b_sc, b_sb = C * s, s, N * C * s
+    y = torch.empty((N, C, 2 * d, 2 * h, 2 * w), dtype=bands.dtype, device=bands.device)
+    with _on(bands.device) as st:
+        native.call("fcwdm_idwt3d_fwd", _ptr(bands), _ptr(y), _dtype_code(bands), N, C, 2 * d, 2 * h, 2 * w, b_sn, b_sc,
+                    b_sb, y.stride(0), y.stride(1), float(lll_scale), st)
+    return y
+
+
+class DWT3DFunction(torch.autograd.Function):
+    """Autograd wrapper; backward of the analysis is the synthesis of the 8 upstream gradients
+    (DWT_IDWT_Functions.py:139-156)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        out = dwt3d_planar(x)
+        return tuple(out[i] for i in range(8))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        g = torch.stack([gi.contiguous() for gi in grads], dim=0)
+        return idwt3d_planar(g)
+
+
+class IDWT3DFunction(torch.autograd.Function):
+    """Backward of the synthesis is the analysis of the upstream gradient (DWT_IDWT_Functions.py:184-208)."""
+
+    @staticmethod
+    def forward(ctx, *bands):
+        shapes = {tuple(b.shape) for b in bands}
+        if len(shapes) != 1:
+            raise FcwdmError(f"IDWT_3D: the 8 sub-bands must share one shape, got {sorted(shapes)}")
+        return idwt3d_planar(torch.stack([b.contiguous() for b in bands], dim=0))
+
+    @staticmethod
+    def backward(ctx, grad):
+        out = dwt3d_planar(grad.contiguous())
+        return tuple(out[i] for i in range(8))
+
+
+# ----------------------------------------------------------------------------------------------------
+# channels-last (bf16) building blocks used by the denoiser
+# ----------------------------------------------------------------------------------------------------
+def dwt3d_cl(x, dims, C, lll, hi, lll_bias=None, lll_scale=1.0 / 3.0, hi_scale=1.0, hi_sb=None):
+    """x: cl buffer (voxels, ld) for dims=(N,D,H,W).  lll / hi: destination cl buffers (hi may be None)."""
+    N, D, H, W = dims
+    with _on(x.device) as st:
+        native.call("fcwdm_dwt3d_cl", _ptr(x), x.stride(0), _ptr(lll), lll.stride(0), _ptr(hi),
+                    hi.stride(-2) if hi is not None else 0,
+                    (hi_sb if hi_sb is not None else (hi.stride(0) if hi is not None else 0)), _ptr(lll_bias), N, D, H, W,
+                    C, float(lll_scale), float(hi_scale), st)
+
+
+def idwt3d_cl(lll, hi, dims_out, C, y, bias=None, lll_scale=3.0):
+    N, D, H, W = dims_out
+    with _on(y.device) as st:
+        native.call("fcwdm_idwt3d_cl", _ptr(lll), lll.stride(0), _ptr(hi), hi.stride(-2), hi.stride(0), _ptr(y),
+                    y.stride(0), _ptr(bias), N, D, H, W, C, float(lll_scale), st)
+
+
+def planar_to_cl(src, dst, C):
+    """src (N,C,...) f32 planar -> dst cl bf16 (N*S, ld) channels [0, C)."""
+    N = src.shape[0]
+    S = src[0, 0].numel()
+    src = src.contiguous()
+    with _on(src.device) as st:
+        native.call("fcwdm_planar_to_cl", _ptr(src), _ptr(dst), dst.stride(0), N, C, S, st)
+
+
+def cl_to_planar(src, dst, C):
+    N = dst.shape[0]
+    S = dst[0, 0].numel()
+    with _on(dst.device) as st:
+        native.call("fcwdm_cl_to_planar", _ptr(src), src.stride(0), _ptr(dst), N, C, S, st)
+
+
+def groupnorm_silu(x, y, stats, gamma, beta, N, S, C, G, eps=1e-5, silu=True):
+    with _on(x.device) as st:
+        native.call("fcwdm_groupnorm_stats", _ptr(x), x.stride(0), _ptr(stats), N, S, C, G, st)
+        native.call("fcwdm_groupnorm_apply", _ptr(x), x.stride(0), _ptr(y), y.stride(0), _ptr(stats), _ptr(gamma),
+                    _ptr(beta), N, S, C, G, float(eps), 1 if silu else 0, st)
+
+
+def timestep_embedding(t, out, dim, max_period=10000.0):
+    with _on(t.device) as st:
+        native.call("fcwdm_timestep_embedding", _ptr(t), _ptr(out), t.shape[0], dim, float(max_period), st)
+
+
+def linear(x, W, b, y, act_in=0, act_out=0):
+    N, K = x.shape
+    M = W.shape[0]
+    with _on(x.device) as st:
+        native.call("fcwdm_linear", _ptr(x), _ptr(W), _ptr(b), _ptr(y), N, K, M, act_in, act_out, st)
+
+
+def conv3d_packed_elems(cout, cin, k):
+    return native.load().fcwdm_conv3d_packed_elems(cout, cin, k)
+
+
+def conv3d_pack_weights(w):
+    """w: (Cout, Cin, k, k, k) float32 CUDA -> packed bf16 [k^3][Cout_p][Cin_p]."""
+    _need_cuda(w, "conv3d_pack_weights")
+    cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+    wp = torch.empty(conv3d_packed_elems(cout, cin, k), dtype=torch.bfloat16, device=w.device)
+    w = w.detach().float().contiguous()
+    with _on(w.device) as st:
+        native.call("fcwdm_conv3d_pack_weights", _ptr(w), _ptr(wp), cout, cin, k, st)
+    return wp
+
+
+def conv3d_cl(x, wp, bias, y, dims, cin, cout, k, chan_bias=None, residual=None):
+    """x, y, residual: cl bf16 buffers (voxels, ld).  dims = (N, D, H, W)."""
+    N, D, H, W = dims
+    with _on(x.device) as st:
+        native.call("fcwdm_conv3d_fwd", _ptr(x), x.stride(0), _ptr(wp), _ptr(bias), _ptr(chan_bias), _ptr(residual),
+                    residual.stride(0) if residual is not None else 0, _ptr(y), y.stride(0), N, D, H, W, cin, cout, k, st)
+
+
+# ----------------------------------------------------------------------------------------------------
+# diffusion step
+# ----------------------------------------------------------------------------------------------------
+def p_sample_step(model_out, x_t, noise, coef, t, clip_denoised=True, predict_xstart=True, want_pred=True,
+                  model_out_cl_ld=0, x_prev_cl=None):
+    """One fused reverse step.  model_out: planar f32 (N,8,d,h,w) or (model_out_cl_ld > 0) a cl bf16 buffer.
+    Returns (x_prev, pred_xstart or None)."""
+    _need_cuda(x_t, "p_sample")
+    N, C, d, h, w = x_t.shape
+    assert C == 8, "the wavelet-domain sample has 8 sub-band channels"
+    x_t = x_t.contiguous()
+    noise = noise.contiguous()
+    if model_out_cl_ld == 0:
+        model_out = model_out.contiguous()
+    x_prev = torch.empty_like(x_t)
+    pred = torch.empty_like(x_t) if want_pred else None
+    with _on(x_t.device) as st:
+        native.call("fcwdm_p_sample_step", _ptr(model_out), model_out_cl_ld, _ptr(x_t), _ptr(noise), _ptr(x_prev),
+                    _ptr(pred), _ptr(x_prev_cl), x_prev_cl.stride(0) if x_prev_cl is not None else 0, _ptr(coef), _ptr(t),
+                    coef.shape[0], N, d, h, w, 1 if clip_denoised else 0, 1 if predict_xstart else 0, st)
+    return x_prev, pred
+
+
+def q_sample(x_start, noise, coef, t):
+    _need_cuda(x_start, "q_sample")
+    x_start = x_start.contiguous()
+    noise = noise.contiguous()
+    out = torch.empty_like(x_start)
+    N = x_start.shape[0]
+    with _on(x_start.device) as st:
+        native.call("fcwdm_q_sample", _ptr(x_start), _ptr(noise), _ptr(out), _ptr(coef), _ptr(t), coef.shape[0], N,
+                    x_start[0].numel() if N else 0, st)
+    return out
+
+
+def sample_to_image(sample, cond_1=None):
+    """(N,8,d,h,w) wavelet sample -> (N,1,2d,2h,2w) image, clamped to [0,1] and masked where cond_1 == 0
+    (scripts/sample.py:113-125)."""
+    _need_cuda(sample, "sample_to_image")
+    sample = sample.contiguous()
+    N, C, d, h, w = sample.shape
+    assert C == 8
+    img = torch.empty((N, 1, 2 * d, 2 * h, 2 * w), dtype=torch.float32, device=sample.device)
+    if cond_1 is not None:
+        cond_1 = cond_1.contiguous()
+        assert cond_1.numel() == img.numel()
+    with _on(sample.device) as st:
+        native.call("fcwdm_sample_to_image", _ptr(sample), _ptr(cond_1), _ptr(img), N, d, h, w, st)
+    return img

@@ -1,0 +1,173 @@
+/*
+ * fcwdm.h -- C-ABI of libfcwdm.so: hand-written sm_100a (B200) kernels for the fast-cwdm hot path.
+ *
+ * The reference (tsereda/fast-cwdm) has no native code and no FFI: every operator below replaces a chain
+ * of PyTorch calls in the reference's Python (cited per function as path:line relative to the reference
+ * root).  The binding a maintainer adds is the ctypes stub shown in INTEGRATION.md
+ * (fast-cwdm_b200/fcwdm/native.py is that stub).
+ *
+ * Conventions
+ *   - plain C types only: device pointers (void* / typed pointers), int64_t sizes and strides (in ELEMENTS),
+ *     float scalars, `stream` = a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns 0 on success or a negative FCWDM_ERR_* code and never throws;
+ *     fcwdm_last_error() returns a thread-local description of the last failure;
+ *   - nothing is allocated and nothing synchronises: the caller owns all memory, outputs are preallocated,
+ *     work is enqueued on `stream`; functions are re-entrant per stream;
+ *   - "planar" = the reference's NCDHW layout (W fastest); "cl" = channels-last NDHWC (C fastest), the
+ *     layout the denoiser keeps internally in bf16;
+ *   - Haar band order everywhere: LLL, LLH, LHL, LHH, HLL, HLH, HHL, HHH; letters are the filters on
+ *     (D, H, W) (DWT_IDWT/DWT_IDWT_Functions.py:128-136).
+ */
+#ifndef FCWDM_H_
+#define FCWDM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCWDM_VERSION 100 /* 0.1.0 */
+
+enum fcwdm_dtype { FCWDM_F32 = 0, FCWDM_BF16 = 1 };
+
+enum fcwdm_status {
+    FCWDM_OK = 0,
+    FCWDM_ERR_INVALID = -1,     /* bad argument (null pointer, odd size, negative dim ...) */
+    FCWDM_ERR_UNSUPPORTED = -2, /* valid in the reference, not implemented by this kernel */
+    FCWDM_ERR_CUDA = -3,        /* a CUDA runtime / driver call failed; see fcwdm_last_error() */
+    FCWDM_ERR_ARCH = -4         /* device is not sm_100 */
+};
+
+int fcwdm_version(void);
+const char* fcwdm_last_error(void);
+/* Idempotent per device: checks compute capability 10.x, resolves the driver entry point used to encode
+ * TMA descriptors and raises the dynamic shared-memory limit of the conv kernels. */
+int fcwdm_init(int device);
+
+/* ------------------------------------------------------------------------------------------------------
+ * K1 / K2: 3-D Haar DWT / IDWT, planar (NCDHW) tensors.
+ * Replaces DWT_3D.forward + DWTFunction_3D (DWT_IDWT/DWT_IDWT_layer.py:520-531,
+ * DWT_IDWT_Functions.py:115-156) and IDWT_3D.forward + IDWTFunction_3D (layer.py:624-646,
+ * Functions.py:159-208): 14 band-matrix matmuls become one 2x2x2 butterfly pass.  Each is the other's
+ * autograd backward.
+ *
+ * x: (N, C, D, H, W) with spatial dims contiguous; element (n,c,d,h,w) at x[n*x_sn + c*x_sc + (d*H+h)*W+w].
+ * bands: band b of (n,c) starts at out[n*o_sn + c*o_sc + b*o_sb], spatial (D/2,H/2,W/2) contiguous.
+ *   8 separate tensors stacked as (8,N,C,d,h,w): o_sb = N*C*d*h*w, o_sn = C*d*h*w, o_sc = d*h*w.
+ *   channel-concatenated (N, 8*C, d,h,w) as th.cat([LLL/3, ...], dim=1) with C == 1
+ *   (scripts/sample.py:92-97, gaussian_diffusion.py:1131-1140): o_sb = d*h*w, o_sn = 8*d*h*w.
+ * lll_scale multiplies the LLL band on output (DWT: 1 or 1/3) / on input (IDWT: 1 or 3).
+ * D, H, W must be even (the reference's matrices floor odd sizes, layer.py:466-494; odd sizes are rejected
+ * here with FCWDM_ERR_UNSUPPORTED).
+ * ---------------------------------------------------------------------------------------------------- */
+int fcwdm_dwt3d_fwd(const void* x, void* bands, int dtype, int64_t N, int64_t C, int64_t D, int64_t H,
+                    int64_t W, int64_t x_sn, int64_t x_sc, int64_t o_sn, int64_t o_sc, int64_t o_sb,
+                    float lll_scale, void* stream);
+int fcwdm_idwt3d_fwd(const void* bands, void* y, int dtype, int64_t N, int64_t C, int64_t D, int64_t H,
+                     int64_t W, int64_t b_sn, int64_t b_sc, int64_t b_sb, int64_t y_sn, int64_t y_sc,
+                     float lll_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Channels-last bf16 DWT / IDWT used inside the denoiser (Downsample / Upsample / WaveletDownsample,
+ * guided_diffusion/wunet.py:40-145).
+ * x: (N, D, H, W, C) bf16, voxel stride x_ld (>= C).  C % 8 == 0.
+ * dwt: LLL -> lll[voxel*lll_ld + c] * lll_scale (+ lll_bias[n*C + c] if non-null: the timestep-embedding
+ *      add that follows the down-sampling, wunet.py:262);
+ *      band b=1..7 -> hi[(b-1)*hi_sb + voxel*hi_ld + c] * hi_scale; hi == NULL skips them (x_upd branch,
+ *      wunet.py:241, which discards the 7 bands).
+ *      WaveletDownsample's cat(...)/3 (wunet.py:143-144): lll = buf, hi = buf + C, hi_sb = C,
+ *      lll_ld = hi_ld = 8*C, both scales 1/3.
+ * idwt: y[voxel*y_ld + c] = IDWT(lll*lll_scale, hi...) (+ bias[n*C + c]).
+ * ---------------------------------------------------------------------------------------------------- */
+int fcwdm_dwt3d_cl(const void* x, int64_t x_ld, void* lll, int64_t lll_ld, void* hi, int64_t hi_ld,
+                   int64_t hi_sb, const float* lll_bias, int64_t N, int64_t D, int64_t H, int64_t W,
+                   int64_t C, float lll_scale, float hi_scale, void* stream);
+int fcwdm_idwt3d_cl(const void* lll, int64_t lll_ld, const void* hi, int64_t hi_ld, int64_t hi_sb,
+                    void* y, int64_t y_ld, const float* bias, int64_t N, int64_t D, int64_t H, int64_t W,
+                    int64_t C, float lll_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * K3: fused reverse-diffusion step.  Replaces process_xstart + q_posterior_mean_variance + the sampling
+ * line of p_sample (guided_diffusion/gaussian_diffusion.py:335-355, 244-267, 565-573) and the six
+ * _extract_into_tensor gathers (:1246-1263) with one elementwise pass:
+ *   x0   = model_out (START_X) or coef[t][3]*x_t - coef[t][4]*model_out (EPSILON, :390-395)
+ *   x0   = DWT(clamp(IDWT(x0; LLL*3), 0, 1)); LLL/3           if clip_denoised
+ *   mean = coef[t][0]*x0 + coef[t][1]*x_t
+ *   x_prev = mean + coef[t][2]*noise        (coef[t][2] = exp(0.5*logvar[t]) * (t != 0), host-prepared)
+ * coef: device float [T][5]; t: device int64 [N] (per-sample timestep, no host sync).
+ * model_out: planar f32 (N,8,d,h,w) when mo_cl_ld == 0, else channels-last bf16 with voxel stride mo_cl_ld.
+ * x_t, noise, x_prev, pred_xstart (optional): planar f32 (N,8,d,h,w).
+ * x_prev_cl (optional): bf16 channels-last copy of x_prev written to x_prev_cl[voxel*xp_cl_ld + band], the
+ * first 8 channels of the persistent denoiser input (replaces th.cat([x, cond]), :297).
+ * ---------------------------------------------------------------------------------------------------- */
+int fcwdm_p_sample_step(const void* model_out, int64_t mo_cl_ld, const float* x_t, const float* noise,
+                        float* x_prev, float* pred_xstart, void* x_prev_cl, int64_t xp_cl_ld,
+                        const float* coef, const int64_t* t, int64_t T, int64_t N, int64_t d, int64_t h,
+                        int64_t w, int clip_denoised, int predict_xstart, void* stream);
+
+/* q_sample (gaussian_diffusion.py:224-242): out = coef[t][0]*x_start + coef[t][1]*noise, any shape with
+ * `per_sample` elements per batch entry; coef: device float [T][2]. */
+int fcwdm_q_sample(const float* x_start, const float* noise, float* out, const float* coef,
+                   const int64_t* t, int64_t T, int64_t N, int64_t per_sample, void* stream);
+
+/* Final image-space step of scripts/sample.py:113-131: IDWT(LLL*3) of the (N,8,d,h,w) planar sample,
+ * clamp to [0,1] (the two masked writes), zero where cond_1 == 0 (cond_1 may be NULL), written as planar
+ * f32 (N,1,2d,2h,2w).  The [..., :155] crop is a view taken by the caller. */
+int fcwdm_sample_to_image(const float* sample, const float* cond_1, float* image, int64_t N, int64_t d,
+                          int64_t h, int64_t w, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Layout / precision converters at the denoiser boundary (the reference is NCDHW fp32 end to end).
+ * planar f32 (N,C,D,H,W) -> cl bf16 written at dst[voxel*dst_ld + c] for c < C, and back.
+ * ---------------------------------------------------------------------------------------------------- */
+int fcwdm_planar_to_cl(const float* src, void* dst, int64_t dst_ld, int64_t N, int64_t C, int64_t S,
+                       void* stream);
+int fcwdm_cl_to_planar(const void* src, int64_t src_ld, float* dst, int64_t N, int64_t C, int64_t S,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * K4: GroupNorm32 (+SiLU).  Replaces nn.GroupNorm in fp32 + nn.SiLU (guided_diffusion/nn.py:17-19,
+ * wunet.py:186-187,210-211,702-703).  x, y: cl bf16 (N, S voxels, C), voxel stride ld; statistics in fp32
+ * per thread, fp64 across blocks.  stats: device double [N][G][2] (sum, sum of squares), zeroed by
+ * fcwdm_groupnorm_stats itself.  C % 8 == 0, C % G == 0, (C/G) in {1,2,4,8,...}.
+ * ---------------------------------------------------------------------------------------------------- */
+int fcwdm_groupnorm_stats(const void* x, int64_t ld, double* stats, int64_t N, int64_t S, int64_t C,
+                          int64_t G, void* stream);
+int fcwdm_groupnorm_apply(const void* x, int64_t x_ld, void* y, int64_t y_ld, const double* stats,
+                          const float* gamma, const float* beta, int64_t N, int64_t S, int64_t C, int64_t G,
+                          float eps, int silu, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Timestep path: sinusoidal embedding (nn.py:103-121) and small dense layers (time_embed, emb_layers;
+ * wunet.py:472-475, 203-206).  y[n][m] = act_out( b[m] + sum_k act_in(x[n][k]) * W[m][k] ), fp32,
+ * act: 0 = identity, 1 = SiLU.
+ * ---------------------------------------------------------------------------------------------------- */
+int fcwdm_timestep_embedding(const int64_t* t, float* out, int64_t N, int64_t dim, float max_period,
+                             void* stream);
+int fcwdm_linear(const float* x, const float* W, const float* b, float* y, int64_t N, int64_t K, int64_t M,
+                 int act_in, int act_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * K5: 3-D convolution, stride 1, "same" zero padding, kernel 3x3x3 or 1x1x1, as a tcgen05 implicit GEMM
+ * (bf16 operands staged by TMA, fp32 accumulation in TMEM).  Replaces nn.Conv3d -> cuDNN
+ * (guided_diffusion/nn.py:22-32; call sites wunet.py:139,188,213,220,483,704).
+ *
+ * fcwdm_conv3d_pack_weights: w (Cout, Cin, k, k, k) f32 device -> wp [k^3][Cout_p][Cin_p] bf16 with
+ *   Cin_p = round_up(Cin, 64), Cout_p = round_up(Cout, 16), zero padded (query sizes with
+ *   fcwdm_conv3d_packed_elems).
+ * fcwdm_conv3d_fwd: x cl bf16 (N,D,H,W, x_ld >= Cin_p channels readable; channels Cin..Cin_p-1 must be
+ *   finite, they meet zero weights), y cl bf16 (N,D,H,W,Cout) with voxel stride y_ld;
+ *   y = conv(x, w) + bias[c] (+ chan_bias[n*Cout + c]: the timestep-embedding add, wunet.py:262)
+ *       (+ residual[voxel*res_ld + c]: the ResBlock skip add, wunet.py:266, or `input_pyramid + h`, :759).
+ * ---------------------------------------------------------------------------------------------------- */
+int64_t fcwdm_conv3d_packed_elems(int64_t Cout, int64_t Cin, int ksize);
+int fcwdm_conv3d_pack_weights(const float* w, void* wp, int64_t Cout, int64_t Cin, int ksize, void* stream);
+int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, const float* bias, const float* chan_bias,
+                     const void* residual, int64_t res_ld, void* y, int64_t y_ld, int64_t N, int64_t D,
+                     int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCWDM_H_ */

@@ -1,0 +1,135 @@
+"""Pins the oracle (oracle/*.py) against fixtures produced by the unmodified reference
+(oracle/make_golden.py).  CPU only."""
+import numpy as np
+import torch
+
+from oracle import diffusion as od
+from oracle import haar
+from oracle import wunet as ow
+from oracle.make_golden import SMALL_CFG, toy_model
+
+
+def test_haar_kat(golden):
+    g = golden("haar")
+    bands = haar.dwt3d(np.arange(8, dtype=np.float32).reshape(1, 1, 2, 2, 2))
+    got = np.array([float(b.ravel()[0]) for b in bands], dtype=np.float32)
+    np.testing.assert_allclose(got, g["kat_bands"], atol=1e-6)
+    # SURVEY.md section 4 KAT values
+    np.testing.assert_allclose(got[[0, 1, 2, 4]], [9.899494, -1.414213, -2.828427, -5.656854], atol=2e-6)
+
+
+def test_haar_bands_and_roundtrip(golden):
+    g = golden("haar")
+    bands = haar.dwt3d(g["x"])
+    for i, b in enumerate(bands):
+        np.testing.assert_allclose(b, g["bands"][i], rtol=0, atol=4e-7)
+    np.testing.assert_allclose(haar.idwt3d(*bands), g["roundtrip"], rtol=0, atol=5e-7)
+    np.testing.assert_allclose(haar.idwt3d(*bands), g["x"], rtol=0, atol=5e-7)
+
+
+def test_haar_backward_is_idwt(golden):
+    g = golden("haar")
+    np.testing.assert_allclose(haar.idwt3d(*g["grad_bands"]), g["grad_x"], rtol=0, atol=2e-6)
+
+
+def test_haar_closed_form(golden):
+    g = golden("haar")
+    ref = haar.dwt3d_butterfly_f64(g["x"])
+    for a, b in zip(haar.dwt3d(g["x"]), ref):
+        np.testing.assert_allclose(a, b, rtol=0, atol=5e-7)
+
+
+def test_schedules(golden):
+    g = golden("schedules")
+    np.testing.assert_array_equal(od.named_beta_schedule("linear", 10, "sampled"), g["sampled10"])
+    np.testing.assert_array_equal(od.named_beta_schedule("linear", 20, "direct"), g["direct20"])
+    np.testing.assert_array_equal(od.named_beta_schedule("linear", 1000, "direct"), g["direct1000"])
+    np.testing.assert_allclose(od.named_beta_schedule("cosine", 50), g["cosine50"], rtol=1e-15)
+    assert sorted(od.space_timesteps(1000, "100")) == list(g["space_1000_100"])
+    assert sorted(od.space_timesteps(1000, "ddim50")) == list(g["space_1000_ddim50"])
+    assert sorted(od.space_timesteps(300, [10, 15, 20])) == list(g["space_300_10_15_20"])
+    assert sorted(od.space_timesteps(1000, "10,10,10")) == list(g["space_1000_10_10_10"])
+    betas, tmap = od.respaced_betas(od.named_beta_schedule("linear", 1000, "direct"), od.space_timesteps(1000, "100"))
+    np.testing.assert_array_equal(betas, g["respaced100_betas"])
+    assert tmap == list(g["respaced100_map"])
+    b10, m10 = od.respaced_betas(od.named_beta_schedule("linear", 10, "sampled"), od.space_timesteps(10, [10]))
+    assert m10 == list(g["d10_map"])
+    tab = od.Tables(b10)
+    for name in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
+                 "sqrt_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                 "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1",
+                 "posterior_mean_coef2"):
+        np.testing.assert_array_equal(getattr(tab, name), g["d10_" + name], err_msg=name)
+
+
+def _tab10():
+    b10, m10 = od.respaced_betas(od.named_beta_schedule("linear", 10, "sampled"), od.space_timesteps(10, [10]))
+    return od.Tables(b10), m10
+
+
+def test_p_sample_and_q_sample(golden):
+    g = golden("diffusion")
+    tab, tmap = _tab10()
+    x, cond = torch.from_numpy(g["x"]), torch.from_numpy(g["cond"])
+    for tval in (9, 4, 0):
+        t = torch.tensor([tval, tval])
+        torch.manual_seed(100 + tval)
+        out = od.p_sample(tab, toy_model, x, t, cond=cond, timestep_map=tmap)
+        np.testing.assert_allclose(out["pred_xstart"].numpy(), g[f"p_sample_t{tval}_pred_xstart"], atol=2e-6)
+        np.testing.assert_allclose(out["sample"].numpy(), g[f"p_sample_t{tval}_sample"], atol=3e-6)
+    q = od.q_sample(tab, x, torch.from_numpy(g["q_t"]), torch.from_numpy(g["q_noise"]))
+    np.testing.assert_allclose(q.numpy(), g["q_sample"], atol=1e-6)
+
+
+def test_p_sample_loop(golden):
+    g = golden("diffusion")
+    tab, tmap = _tab10()
+    torch.manual_seed(7)
+    out = od.p_sample_loop(tab, toy_model, torch.from_numpy(g["x"]), cond=torch.from_numpy(g["cond"]), timestep_map=tmap)
+    np.testing.assert_allclose(out.numpy(), g["loop_final"], atol=2e-5)
+
+
+def test_training_losses(golden):
+    g = golden("diffusion")
+    tab, tmap = _tab10()
+    batch = {k: torch.from_numpy(g["tl_" + k]) for k in ("t1n", "t1c", "t2w", "t2f")}
+    torch.manual_seed(11)
+    terms, mo, mo_idwt = od.training_losses(tab, toy_model, batch, torch.from_numpy(g["tl_t"]), timestep_map=tmap)
+    np.testing.assert_allclose(mo.numpy(), g["tl_model_output"], atol=3e-6)
+    np.testing.assert_allclose(mo_idwt.numpy(), g["tl_model_output_idwt"], atol=5e-6)
+    np.testing.assert_allclose(terms["mse_wav"].numpy(), g["tl_mse_wav"], rtol=1e-5)
+
+
+def test_sample_postprocess(golden):
+    g = golden("diffusion")
+    out = od.sample_postprocess(torch.from_numpy(g["post_in"]), torch.from_numpy(g["post_cond1"]))
+    assert out.shape == (1, 8, 12, 155)
+    np.testing.assert_allclose(out.numpy(), g["post_out"], atol=2e-6)
+
+
+def _small_sd(golden):
+    g = golden("wunet_small")
+    shapes = {str(k): tuple(int(v) for v in str(s).split(",")) for k, s in zip(g["keys"], g["shapes"])}
+    return ow.tie_output_blocks(ow.seeded_state_dict(shapes, seed=0), len(SMALL_CFG["channel_mult"]))
+
+
+def test_wunet_small(golden):
+    g = golden("wunet_small")
+    sd = _small_sd(golden)
+    y = ow.wunet_forward(sd, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), model_channels=32,
+                         channel_mult=(1, 2))
+    err = (y.numpy() - g["y"])
+    assert np.abs(err).max() < 5e-5 * max(1.0, np.abs(g["y"]).max()), np.abs(err).max()
+
+
+def test_loop_small(golden):
+    g = golden("loop_small")
+    sd = _small_sd(golden)
+    tab = od.Tables(g["betas"])
+    model = lambda x, t: ow.wunet_forward(sd, x, t, model_channels=32, channel_mult=(1, 2))
+    torch.manual_seed(5)
+    img = torch.from_numpy(g["x"])
+    cond = torch.from_numpy(g["cond"])
+    for k, i in enumerate(reversed(range(tab.num_timesteps))):
+        img = od.p_sample(tab, model, img, torch.tensor([i]), cond=cond, timestep_map=list(g["tmap"]))["sample"]
+        np.testing.assert_allclose(img.numpy(), g["samples"][k], atol=2e-4)
