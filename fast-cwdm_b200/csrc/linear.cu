@@ -15,7 +15,8 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* 
     float v = 0.f;  // odd dim: trailing zero column (nn.py:119-120)
     if (j < 2 * half) {
         const int k = j < half ? j : j - half;
-        const float freq = expf(-logf(max_period) * (float)k / (float)half);
+        // exp evaluated in fp64 and rounded once: the correctly rounded fp32 value of the reference's fp32 exp argument
+        const float freq = (float)exp((double)(-logf(max_period) * (float)k / (float)half));
         const float arg = (float)t[n] * freq;
         v = j < half ? cosf(arg) : sinf(arg);   // cat([cos, sin]) (nn.py:118)
     }

@@ -1,0 +1,227 @@
+"""Execution engine of the wavelet U-Net denoiser on fcwdm kernels.
+
+Walks a ``guided_diffusion.wunet.WavUNetModel`` module tree (the parameter container with the reference's
+346 state-dict keys) and runs its forward as a fixed sequence of C-ABI launches on channels-last bf16
+activation buffers:
+
+    conv3d (tcgen05 implicit GEMM, bias / timestep-embedding / residual fused in the epilogue)
+    GroupNorm + SiLU (two HBM passes)           Haar DWT / IDWT (one pass, /3, x3, embedding add fused)
+
+The launch sequence contains no host synchronisation and no allocation-dependent control flow, so it can be
+captured into a CUDA graph (see fcwdm.sampler).  Weights are repacked to bf16 [tap][C_out][C_in] lazily and
+again whenever a parameter is modified in place (load_state_dict, optimizer step).
+"""
+import math
+
+import torch
+
+from . import ops
+from .native import FcwdmError
+
+
+def _ld(c):
+    return (c + 63) // 64 * 64
+
+
+class _Packed:
+    __slots__ = ("wp", "bias", "cin", "cout", "k")
+
+
+class WavUNetEngine:
+    def __init__(self, model):
+        self.model = model
+        self._sig = None
+        self._conv = {}
+        self._f32 = {}
+        self._device = None
+
+    # ------------------------------------------------------------------ weights
+    def _signature(self):
+        return tuple((id(p), p._version, p.device) for p in self.model.parameters())
+
+    def prepare(self, device):
+        sig = self._signature()
+        if sig == self._sig and self._device == device:
+            return
+        self._conv.clear()
+        self._f32.clear()
+        for mod in self.model.modules():
+            if isinstance(mod, torch.nn.Conv3d):
+                k = mod.kernel_size[0]
+                if mod.kernel_size != (k, k, k) or k not in (1, 3) or mod.stride != (1, 1, 1) or \
+                        mod.padding != (k // 2,) * 3 or mod.groups != 1 or mod.dilation != (1, 1, 1):
+                    raise NotImplementedError(f"conv3d configuration not supported by the fcwdm kernel: {mod}")
+                if not mod.weight.is_cuda:
+                    raise FcwdmError("WavUNetModel parameters are on the CPU; call model.to(cuda_device) first "
+                                     "(the fcwdm denoiser has no CPU path)")
+                pk = _Packed()
+                pk.wp = ops.conv3d_pack_weights(mod.weight)
+                pk.bias = mod.bias.detach().float().contiguous() if mod.bias is not None else None
+                pk.cout, pk.cin, pk.k = mod.out_channels, mod.in_channels, k
+                self._conv[id(mod)] = pk
+        self._sig = sig
+        self._device = device
+
+    def _p32(self, p):
+        """fp32 contiguous view of a (GroupNorm / Linear) parameter."""
+        t = self._f32.get(id(p))
+        if t is None:
+            t = p.detach().float().contiguous()
+            self._f32[id(p)] = t
+        return t
+
+    # ------------------------------------------------------------------ building blocks
+    @staticmethod
+    def _buf(rows, c, device, ld=None):
+        ld = ld or _ld(c)
+        if ld == c:
+            return torch.empty((rows, ld), dtype=torch.bfloat16, device=device)
+        return torch.zeros((rows, ld), dtype=torch.bfloat16, device=device)   # pad channels feed zero weights
+
+    def _conv3d(self, mod, x, N, dims, chan_bias=None, residual=None, out_ld=None):
+        pk = self._conv[id(mod)]
+        rows = N * dims[0] * dims[1] * dims[2]
+        y = self._buf(rows, pk.cout, x.device, out_ld)
+        ops.conv3d_cl(x, pk.wp, pk.bias, y, (N,) + tuple(dims), pk.cin, pk.cout, pk.k, chan_bias=chan_bias,
+                      residual=residual)
+        return y
+
+    def _gn_silu(self, gn, x, N, S, silu=True):
+        C = gn.num_channels
+        y = self._buf(N * S, C, x.device)
+        stats = torch.empty((N, gn.num_groups, 2), dtype=torch.float64, device=x.device)
+        ops.groupnorm_silu(x, y, stats, self._p32(gn.weight), self._p32(gn.bias), N, S, C, gn.num_groups, gn.eps, silu)
+        return y
+
+    def _emb_out(self, blk, emb):
+        lin = blk.emb_layers[1]
+        out = torch.empty((emb.shape[0], lin.out_features), dtype=torch.float32, device=emb.device)
+        ops.linear(emb, self._p32(lin.weight), self._p32(lin.bias), out, act_in=1, act_out=0)   # Linear(SiLU(emb))
+        return out
+
+    def _resblock(self, blk, x, skip, emb, N, dims):
+        """ResBlock.forward (reference wunet.py:223-269).  Returns (out, skip_out, dims_out)."""
+        S = dims[0] * dims[1] * dims[2]
+        dev = x.device
+        cin, cout = blk.channels, blk.out_channels
+        emb_out = self._emb_out(blk, emb)
+        a = self._gn_silu(blk.in_layers[0], x, N, S)
+        skip_out = skip
+        if blk.down:
+            h_full = self._conv3d(blk.in_layers[2], a, N, dims)
+            d2 = (dims[0] // 2, dims[1] // 2, dims[2] // 2)
+            s2 = d2[0] * d2[1] * d2[2]
+            h = self._buf(N * s2, cout, dev)
+            hi = torch.empty((7, N * s2, _ld(cout)), dtype=torch.bfloat16, device=dev) if _ld(cout) == cout else \
+                torch.zeros((7, N * s2, _ld(cout)), dtype=torch.bfloat16, device=dev)
+            # h, hSkip = Downsample(h): LLL/3 (+ emb, :262) and the 7 high bands (:118-121, :240)
+            ops.dwt3d_cl(h_full, (N,) + tuple(dims), cout, h, hi, lll_bias=emb_out, lll_scale=1.0 / 3.0)
+            xs = self._buf(N * s2, cin, dev)
+            ops.dwt3d_cl(x, (N,) + tuple(dims), cin, xs, None, lll_scale=1.0 / 3.0)      # x_upd: LLL/3 only (:241)
+            x, dims, S, skip_out = xs, d2, s2, hi
+        elif blk.up:
+            if skip is None:
+                raise FcwdmError("up-sampling ResBlock reached without stored high-frequency sub-bands")
+            h_low = self._conv3d(blk.in_layers[2], a, N, dims)
+            d2 = (dims[0] * 2, dims[1] * 2, dims[2] * 2)
+            s2 = d2[0] * d2[1] * d2[2]
+            h = self._buf(N * s2, cout, dev)
+            ops.idwt3d_cl(h_low, skip, (N,) + d2, cout, h, bias=emb_out, lll_scale=3.0)   # IDWT(3h, skip) + emb
+            xu = self._buf(N * s2, cin, dev)
+            ops.idwt3d_cl(x, skip, (N,) + d2, cin, xu, bias=None, lll_scale=3.0)          # IDWT(3x, skip)
+            x, dims, S, skip_out = xu, d2, s2, None
+        else:
+            h = self._conv3d(blk.in_layers[2], a, N, dims, chan_bias=emb_out)            # conv + emb (:262)
+        b = self._gn_silu(blk.out_layers[0], h, N, S)
+        if isinstance(blk.skip_connection, torch.nn.Conv3d):
+            x = self._conv3d(blk.skip_connection, x, N, dims)
+        out = self._conv3d(blk.out_layers[3], b, N, dims, residual=x)                    # skip(x) + h (:266)
+        return out, skip_out, dims
+
+    # ------------------------------------------------------------------ whole network
+    def time_embedding(self, t):
+        m = self.model
+        te = torch.empty((t.shape[0], m.model_channels), dtype=torch.float32, device=t.device)
+        ops.timestep_embedding(t, te, m.model_channels)
+        l0, l2 = m.time_embed[0], m.time_embed[2]
+        e1 = torch.empty((t.shape[0], l0.out_features), dtype=torch.float32, device=t.device)
+        ops.linear(te, self._p32(l0.weight), self._p32(l0.bias), e1, act_in=0, act_out=1)
+        e2 = torch.empty((t.shape[0], l2.out_features), dtype=torch.float32, device=t.device)
+        ops.linear(e1, self._p32(l2.weight), self._p32(l2.bias), e2, act_in=0, act_out=0)
+        return e2
+
+    def forward_cl(self, x_cl, t, N, dims, out_ld=None):
+        """x_cl: (N*S, >= round_up(in_channels, 64)) bf16 channels-last; t: (N,) int64 CUDA.
+        Returns the (N*S, out_ld) bf16 channels-last model output.  Mirrors WavUNetModel.forward
+        (reference wunet.py:734-795)."""
+        from guided_diffusion.wunet import ResBlock, WaveletDownsample
+        m = self.model
+        self.prepare(x_cl.device)
+        levels = len(m.channel_mult)
+        for i, dim in enumerate(dims):
+            if dim % (2 ** levels):
+                raise FcwdmError(f"spatial size {tuple(dims)} is not divisible by 2^{levels} (one Haar level per "
+                                 f"channel_mult entry; the reference fails the same way, SURVEY.md fact 3)")
+        emb = self.time_embedding(t)
+        hs = []
+        pyramid, pyr_dims, pyr_c = x_cl, tuple(dims), m.in_channels
+        h, hdims = x_cl, tuple(dims)
+        for module in m.input_blocks:
+            first = module[0]
+            if isinstance(first, WaveletDownsample):
+                # input_pyramid = conv(cat(DWT(pyramid)) / 3) + h   (:142-145, :758-760)
+                d2 = (pyr_dims[0] // 2, pyr_dims[1] // 2, pyr_dims[2] // 2)
+                s2 = d2[0] * d2[1] * d2[2]
+                cat = self._buf(N * s2, 8 * pyr_c, x_cl.device)
+                ops.dwt3d_cl(pyramid, (N,) + pyr_dims, pyr_c, cat[:, :pyr_c], cat[:, pyr_c:], lll_scale=1.0 / 3.0,
+                             hi_scale=1.0 / 3.0, hi_sb=pyr_c)
+                pyramid = self._conv3d(first.conv, cat, N, d2, residual=h)
+                pyr_dims, pyr_c = d2, first.out_ch
+                h = pyramid
+                continue
+            skip = None
+            if isinstance(first, torch.nn.Conv3d):
+                h = self._conv3d(first, h, N, hdims)
+            else:
+                for layer in module:
+                    if not isinstance(layer, ResBlock):
+                        raise NotImplementedError(f"unsupported layer in input_blocks: {type(layer).__name__}")
+                    h, skip, hdims = self._resblock(layer, h, None, emb, N, hdims)
+            hs.append(skip)
+        skip = None
+        for layer in m.middle_block:
+            h, skip, hdims = self._resblock(layer, h, None, emb, N, hdims)
+            skip = None                                                   # `h, skip = h` overwrites with None (:765)
+        for module in m.output_blocks:
+            new_hs = hs.pop()
+            if new_hs is not None:
+                skip = new_hs
+            cur = skip
+            for layer in module:
+                h, cur, hdims = self._resblock(layer, h, cur, emb, N, hdims)
+        for module in m.out_res:
+            for layer in module:
+                h, _, hdims = self._resblock(layer, h, None, emb, N, hdims)
+        S = hdims[0] * hdims[1] * hdims[2]
+        a = self._gn_silu(m.out[0], h, N, S)
+        return self._conv3d(m.out[2], a, N, hdims, out_ld=out_ld or max(8, (m.out_channels + 7) // 8 * 8))
+
+    def forward(self, x, timesteps):
+        """Planar fp32 API of the reference: x (N, C, D, H, W), timesteps (N,) -> (N, out_channels, D, H, W)."""
+        m = self.model
+        if not x.is_cuda:
+            raise FcwdmError("WavUNetModel.forward: input is on the CPU; the fcwdm denoiser has no CPU path")
+        if x.dim() != 5 or x.shape[1] != m.in_channels:
+            raise ValueError(f"expected input of shape (N, {m.in_channels}, D, H, W), got {tuple(x.shape)}")
+        if timesteps.is_floating_point():
+            raise NotImplementedError("fractional timesteps (rescale_timesteps=True) are not implemented")
+        N, C, D, H, W = x.shape
+        S = D * H * W
+        with torch.cuda.device(x.device):
+            x_cl = torch.zeros((N * S, _ld(C)), dtype=torch.bfloat16, device=x.device) if _ld(C) != C else \
+                torch.empty((N * S, C), dtype=torch.bfloat16, device=x.device)
+            ops.planar_to_cl(x.float(), x_cl, C)
+            out_cl = self.forward_cl(x_cl, timesteps.to(torch.int64).contiguous(), N, (D, H, W))
+            out = torch.empty((N, m.out_channels, D, H, W), dtype=torch.float32, device=x.device)
+            ops.cl_to_planar(out_cl, out, m.out_channels)
+        return out.to(x.dtype) if x.dtype != torch.float32 else out

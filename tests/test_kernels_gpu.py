@@ -116,7 +116,9 @@ def test_timestep_path():
     out = torch.empty((5, 64), device="cuda")
     ops.timestep_embedding(t, out, 64)
     ref = ow.timestep_embedding(t.cpu(), 64)
-    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=2e-5)
+    # |d cos(t*f)| <= t * ulp(f): the fp32 exp of the frequency may differ by 1 ulp between libms (t <= 999)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=1e-4)
+    np.testing.assert_allclose(out[:3].cpu().numpy(), ref[:3].numpy(), atol=2e-5)
     g = torch.Generator().manual_seed(1)
     x = torch.randn(5, 64, generator=g)
     W = torch.randn(256, 64, generator=g) * 0.1
