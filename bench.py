@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Headline benchmark of the fast-cwdm hot path on B200 (contract: one JSON line on stdout from rank 0).
+
+Workload (BASELINE.json configs[1]): full respaced `p_sample_loop` synthesising one modality from three, batch 1,
+224x224x160 BraTS-shaped synthetic volume, WavUNetModel CFG-W4 (the only WavUNetModel configuration that runs at
+this size) with random-init weights (zero-init convs re-randomised), T = 10 steps of the
+`sampled` schedule (the fast-cwdm setting, tr_job.yml:122).  One "step" = one whole volume: conditioning DWTs,
+T denoising steps (each 74 tcgen05 conv3d + 65 GroupNorm/SiLU + 20 DWT/IDWT + 1 fused posterior update), final
+IDWT + clamp + mask.
+
+  value : volumes/s with the inputs resident in HBM, CUDA-event timed, max over ranks.
+  e2e   : the same through the public per-volume API with pinned HOST buffers: H2D of the three conditioning
+          modalities and the CPU-drawn noise (scripts/sample.py:100) and D2H of the synthesised volume are inside
+          the timed region.
+  roofline : dominant kernel = conv3d 64->64 @112x112x80 (10 launches per denoising step, 60% of the FLOPs), timed
+          alone with CUDA events; peak = measured cuBLAS bf16 burst figure (MEASURED_PEAKS.json).
+  cpu_baseline : the oracle port (oracle/*.py, torch CPU fp32 restatement of the reference) on the host cores.
+
+`--impl reference` times the reference's algorithm on the CPU (the reference is pure Python and does not travel to
+the GPU box, so the oracle port stands in; /root/reference is never read here).
+Multi-GPU: one process per GPU (torchrun), volumes partitioned by rank, no collective on the data path; the only
+communication is the timing barrier / max-reduction.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "fast-cwdm_b200")]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+T_STEPS = 10
+LATENT = (112, 112, 80)
+IMAGE = (224, 224, 160)
+CFG_W4 = dict(image_size=224, in_channels=32, num_channels=64, out_channels=8, channel_mult="1,2,2,4", dims=3,
+              attention_resolutions="", bottleneck_attention=False, resblock_updown=True, use_freq=True,
+              use_scale_shift_norm=False, predict_xstart=True, diffusion_steps=T_STEPS, sample_schedule="sampled",
+              mode="i2i", num_groups=32, num_heads=1, num_res_blocks=2)
+CONV_FLOP_PER_STEP = 3665.0e9            # 74 conv3d per denoiser call, CFG-W4, batch 1
+WORKLOAD = "p_sample_loop T=10 'sampled' i2i, WavUNetModel CFG-W4 (1,2,2,4), batch 1, 224x224x160 volume"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(len(r) > col and r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_model(device):
+    from guided_diffusion.script_util import create_model_and_diffusion, model_and_diffusion_defaults
+    args = model_and_diffusion_defaults()
+    args.update(CFG_W4)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, diffusion = create_model_and_diffusion(**args)
+    g = torch.Generator().manual_seed(0)
+    for p in model.parameters():                       # re-randomise the zero-initialised convs
+        if float(p.detach().abs().max()) == 0.0:
+            p.data.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    model.to(device).eval()
+    return model, diffusion
+
+
+def synth_volume(seed):
+    """BraTS-shaped synthetic case: 4 modalities in [0,1) with a zero background border (exercises the mask)."""
+    g = torch.Generator().manual_seed(seed)
+    vol = torch.rand((1, 4) + IMAGE, generator=g)
+    vol[:, :, :8] = 0
+    vol[:, :, :, :8] = 0
+    noise = torch.randn((1, 8) + LATENT, generator=g)
+    return vol, noise
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference algorithm (torch CPU fp32), bounded sample
+# ----------------------------------------------------------------------------------------------------
+def oracle_state():
+    from oracle import wunet as ow
+    from guided_diffusion.wunet import WavUNetModel
+    m = WavUNetModel(image_size=224, in_channels=32, model_channels=64, out_channels=8, num_res_blocks=2,
+                     attention_resolutions=(), channel_mult=(1, 2, 2, 4), dims=3, num_groups=32,
+                     bottleneck_attention=False, resblock_updown=True, use_freq=True)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    return ow.tie_output_blocks(ow.seeded_state_dict(shapes, seed=0, std=0.02), 4)
+
+
+def cpu_step_seconds(sd, depth):
+    """One reference denoising step (U-Net forward + IDWT/clamp/DWT/posterior/noise) on a depth slab of the latent
+    volume, torch CPU, all host threads.  Returns seconds."""
+    from oracle import diffusion as od
+    from oracle import wunet as ow
+    tab = od.Tables(od.named_beta_schedule("linear", T_STEPS, "sampled"))
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((1, 8, depth) + LATENT[1:], generator=g)
+    cond = torch.rand((1, 24, depth) + LATENT[1:], generator=g)
+    model = lambda xin, tt: ow.wunet_forward(sd, xin, tt, model_channels=64, channel_mult=(1, 2, 2, 4))
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        od.p_sample(tab, model, x, torch.tensor([T_STEPS - 1]), cond=cond)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(budget_s=25.0):
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = oracle_state()
+    depth = 16                                           # 1/7 of the latent depth; must be divisible by 2^4
+    dt = cpu_step_seconds(sd, depth)
+    if dt * (LATENT[0] / depth) <= budget_s:             # fast host: time the full-depth step as well
+        depth = LATENT[0]
+        dt = cpu_step_seconds(sd, depth)
+    step_full = dt * (LATENT[0] / depth)
+    return {"value": 1.0 / (T_STEPS * step_full), "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"one reference denoising step (WavUNet fwd + IDWT/clamp/DWT + posterior) on a {depth}-plane "
+                      f"slab of the 112-plane latent, {dt:.2f} s, scaled x{LATENT[0] // depth} x T={T_STEPS}; "
+                      f"host {os.cpu_count()} logical cores"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = oracle_state()
+    total = args.steps + args.warmup
+    depth = 16
+    probe = cpu_step_seconds(sd, depth)                  # also serves as the page-in warm-up
+    if probe * (LATENT[0] / depth) * total <= 240.0:
+        depth = LATENT[0]
+    for _ in range(args.warmup):
+        cpu_step_seconds(sd, depth)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step_seconds(sd, depth)
+    per_step = (time.perf_counter() - t0) / max(1, args.steps)
+    vol_s = 1.0 / (T_STEPS * per_step * (LATENT[0] / depth))
+    sample = (f"each step = one reference denoising step on a {depth}-plane slab of the 112-plane latent "
+              f"({per_step:.2f} s), scaled x{LATENT[0] // depth} x T={T_STEPS} to volumes/s")
+    print(json.dumps({"impl": "reference", "metric": "sampled 224x224x160 volumes/sec", "value": vol_s,
+                      "unit": "volumes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": 1e3 / vol_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "arm": "oracle port on CPU"},
+                      "cpu_baseline": {"value": vol_s, "unit": "volumes/s", "cores": torch.get_num_threads(),
+                                       "kind": "port", "sample": sample},
+                      "e2e": {"value": vol_s, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def time_dominant_kernel(device, iters=20):
+    """conv3d 64->64 3x3x3 @112x112x80 alone: CUDA events on the launching stream, inputs (128 MB) ~ L2 size and
+    a 256 MB L2 flush between launches."""
+    from fcwdm import ops
+    S = LATENT[0] * LATENT[1] * LATENT[2]
+    x = torch.randn((S, 64), device=device).to(torch.bfloat16)
+    w = torch.randn((64, 64, 3, 3, 3), device=device) * 0.02
+    wp = ops.conv3d_pack_weights(w)
+    b = torch.zeros(64, device=device)
+    y = torch.empty((S, 64), dtype=torch.bfloat16, device=device)
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=device)
+    for _ in range(3):
+        ops.conv3d_cl(x, wp, b, y, (1,) + LATENT, 64, 64, 3)
+    total = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.conv3d_cl(x, wp, b, y, (1,) + LATENT, 64, 64, 3)
+        e1.record()
+        e1.synchronize()
+        total += e0.elapsed_time(e1)
+    ms = total / iters
+    flop = 2.0 * S * 64 * 64 * 27
+    return ms, flop
+
+
+def time_haar(device, iters=10):
+    """DWT_3D / IDWT_3D standalone bandwidth (BASELINE metric part 2): 16 x 224x224x160 fp32 = 514 MB in + 514 MB
+    out per launch (>> L2)."""
+    from fcwdm import ops
+    v = torch.rand((1, 16) + IMAGE, device=device)
+    out = {}
+    for name, fn in (("dwt3d", lambda: ops.dwt3d_planar(v)),):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        e1.synchronize()
+        out[name] = 2.0 * v.numel() * 4 / (e0.elapsed_time(e1) / iters * 1e-3) / 1e9
+    bands = ops.dwt3d_planar(v)
+    for _ in range(3):
+        ops.idwt3d_planar(bands)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ops.idwt3d_planar(bands)
+    e1.record()
+    e1.synchronize()
+    out["idwt3d"] = 2.0 * v.numel() * 4 / (e0.elapsed_time(e1) / iters * 1e-3) / 1e9
+    return out
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    from fcwdm import native, pipeline
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the fcwdm hot path has no CPU fallback (use --impl reference "
+                         "for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    peaks = measured_peaks()
+    model, diffusion = build_model(device)
+
+    # every rank owns its own volumes (weak scaling): volume index = rank * (K + W) + i, no collective
+    n_local = args.steps + args.warmup
+    my_ids = pipeline.shard_indices(n_local * world, rank, world)
+    host_vol, host_noise = synth_volume(1000 + my_ids[0])
+    host_vol = host_vol.pin_memory()
+    host_noise = host_noise.pin_memory()
+    host_out = torch.empty((1,) + IMAGE[:2] + (155,), dtype=torch.float32).pin_memory()
+    dev_vol = host_vol.to(device)
+    dev_noise = host_noise.to(device)
+
+    def volume_resident():
+        return pipeline.synthesize(diffusion, model, dev_vol[:, 1:2], dev_vol[:, 2:3], dev_vol[:, 3:4], dev_noise)
+
+    def volume_e2e():
+        v = host_vol.to(device, non_blocking=True)
+        nz = host_noise.to(device, non_blocking=True)
+        img = pipeline.synthesize(diffusion, model, v[:, 1:2], v[:, 2:3], v[:, 3:4], nz)
+        host_out.copy_(img, non_blocking=True)
+        return img
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def timed(fn, k, w):
+        for _ in range(w):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    torch.manual_seed(1234 + rank)
+    clocks = ClockSampler(local)
+    warm = max(args.warmup, 3)
+    timed(volume_resident, 0, warm)                      # lazy init, weight packing, CUDA-graph capture
+    clocks.start()
+    ms_res = timed(volume_resident, args.steps, 0)
+    clk = clocks.stop()
+    sampler = list(diffusion._samplers.values())[0]
+    launches_per_volume = sampler.launches_per_step * T_STEPS + 3 + 2 + 1     # + cond DWTs, x_T/cond layout, image
+    ms_e2e = timed(volume_e2e, args.steps, 1)
+    out = volume_resident()
+    finite = bool(torch.isfinite(out).all())
+
+    result = None
+    if rank == 0:
+        vols = args.steps * world
+        value = vols / (ms_res * 1e-3)
+        e2e = vols / (ms_e2e * 1e-3)
+        h2d = host_vol[:, 1:].numel() * 4 + host_noise.numel() * 4       # 3 modalities actually used + noise
+        d2h = host_out.numel() * 4
+        result = {
+            "metric": "sampled 224x224x160 volumes/sec", "value": value, "unit": "volumes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": f"volumes sharded over {world} GPU(s), no collective",
+                       "l2": "per-step activations ~10 GB >> 126 MB L2 (no flush needed)", "T": T_STEPS,
+                       "denoiser_gflop_per_step": CONV_FLOP_PER_STEP / 1e9, "peaks": peaks["src"],
+                       "output_finite": finite},
+            "e2e": {"value": e2e, "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches_per_volume * args.steps),
+            "clocks": clk,
+            "step_tflops": CONV_FLOP_PER_STEP * T_STEPS * vols / (ms_res * 1e-3) / 1e12,
+        }
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        ms_k, flop = time_dominant_kernel(device)
+        ach = flop / (ms_k * 1e-3) / 1e12
+        result["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                              "frac": ach / peaks["tf_burst"], "traffic": None,
+                              "kernel": "conv3d_igemm_kernel<64,4,3> 64->64 @112x112x80",
+                              "us_per_launch": ms_k * 1e3, "flop_per_launch": flop}
+        hb = time_haar(device)
+        result["secondary"] = {"dwt3d_gbs": hb["dwt3d"], "idwt3d_gbs": hb["idwt3d"], "hbm_peak_gbs": peaks["hbm"],
+                               "dwt3d_frac": hb["dwt3d"] / peaks["hbm"], "idwt3d_frac": hb["idwt3d"] / peaks["hbm"],
+                               "workload": "16 x 224x224x160 fp32 planar, 2*numel*4 bytes per launch"}
+        if world == 1 and not args.no_cpu_baseline:
+            result["cpu_baseline"] = cpu_baseline()
+        else:
+            result["cpu_baseline"] = None
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="fcwdm", choices=["fcwdm", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// Warp-uniform election of one lane (the compiler then keeps the tcgen05 operands in uniform registers instead of
+// wrapping every UTCHMMA in a per-lane serialisation loop, which is what a divergent `lane == 0` branch produces).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -275,57 +286,66 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
             }
         }
     } else if (warp == 2) {
-        // ================================ MMA issuer ================================
-        if (lane == 0) {
-            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
-            // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) |
-                                       ((uint32_t)(128 >> 4) << 24);
-            uint32_t q_base = 0, r = 0, acc_it = 0;
-            for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++acc_it) {
-                const uint32_t as = acc_it % Cfg::ACC_STAGES, aph = (acc_it / Cfg::ACC_STAGES) & 1;
-                mbar_wait(tmem_empty + 8 * as, aph ^ 1);
-                tc_fence_after();
-                const uint32_t acc0 = tmem_base + as * Cfg::ACC_COLS;
-                for (int cb = 0; cb < args.n_cb; ++cb) {
-                    int planes_ready = 0;
-                    for (int kd = 0; kd < KS; ++kd) {
-                        while (planes_ready < kd + TD) {
-                            const uint32_t qq = q_base + planes_ready;
-                            mbar_wait(full_a + 8 * (qq % Cfg::A_SLOTS), (qq / Cfg::A_SLOTS) & 1);
-                            ++planes_ready;
-                        }
-                        tc_fence_after();
-                        for (int kh = 0; kh < KS; ++kh) {
-                            for (int kw = 0; kw < KS; ++kw, ++r) {
-                                const uint32_t st = r % Cfg::B_STAGES;
-                                mbar_wait(full_b + 8 * st, (r / Cfg::B_STAGES) & 1);
-                                tc_fence_after();
-                                const uint32_t b_addr = smem_b + st * Cfg::B_BYTES;
-                                const bool first_tap = (cb == 0) && (kd == 0) && (kh == 0) && (kw == 0);
+        // ================================ MMA issuer (whole warp walks the loops; one elected lane issues) =======
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+        // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+        const uint64_t a_desc_base = make_sw128_desc(smem_a, Cfg::ROWP * 128);
+        const uint64_t b_desc_base = make_sw128_desc(smem_b, 1024);
+        uint32_t q_base = 0, r = 0, acc_it = 0;
+        for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++acc_it) {
+            const uint32_t as = acc_it % Cfg::ACC_STAGES, aph = (acc_it / Cfg::ACC_STAGES) & 1;
+            mbar_wait(tmem_empty + 8 * as, aph ^ 1);
+            tc_fence_after();
+            const uint32_t acc0 = tmem_base + as * Cfg::ACC_COLS;
+            for (int cb = 0; cb < args.n_cb; ++cb) {
+                int planes_ready = 0;
+                for (int kd = 0; kd < KS; ++kd) {
+                    while (planes_ready < kd + TD) {
+                        const uint32_t qq = q_base + planes_ready;
+                        mbar_wait(full_a + 8 * (qq % Cfg::A_SLOTS), (qq / Cfg::A_SLOTS) & 1);
+                        ++planes_ready;
+                    }
+                    // descriptors of the TD planes this kd touches (start-address field is in 16-byte units)
+                    uint64_t a_desc[TD];
+#pragma unroll
+                    for (int j = 0; j < TD; ++j)
+                        a_desc[j] = a_desc_base + (uint64_t)((((q_base + kd + j) % Cfg::A_SLOTS) * Cfg::SLOT_BYTES) >> 4);
+                    for (int kh = 0; kh < KS; ++kh) {
+                        for (int kw = 0; kw < KS; ++kw, ++r) {
+                            const uint32_t st = r % Cfg::B_STAGES;
+                            mbar_wait(full_b + 8 * st, (r / Cfg::B_STAGES) & 1);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t b_desc = b_desc_base + (uint64_t)((st * Cfg::B_BYTES) >> 4);
+                                const uint64_t tap_off = (uint64_t)(((kh * Cfg::ROWP + kw) * 128) >> 4);
+                                const uint32_t first = ((cb == 0) && (kd == 0) && (kh == 0) && (kw == 0)) ? 0u : 1u;
 #pragma unroll
                                 for (int j = 0; j < TD; ++j) {
-                                    const uint32_t qq = q_base + kd + j;
-                                    const uint32_t a_addr = smem_a + (qq % Cfg::A_SLOTS) * Cfg::SLOT_BYTES +
-                                                            (kh * Cfg::ROWP + kw) * 128;
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        umma_bf16(acc0 + j * N_TILE, make_sw128_desc(a_addr + k * 32, Cfg::ROWP * 128),
-                                                  make_sw128_desc(b_addr + k * 32, 1024), idesc,
-                                                  (first_tap && k == 0) ? 0u : 1u);
-                                    }
+                                    const uint64_t ad = a_desc[j] + tap_off;
+                                    umma_bf16(acc0 + j * N_TILE, ad, b_desc, idesc, first);
+                                    umma_bf16(acc0 + j * N_TILE, ad + 2, b_desc + 2, idesc, 1u);
+                                    umma_bf16(acc0 + j * N_TILE, ad + 4, b_desc + 4, idesc, 1u);
+                                    umma_bf16(acc0 + j * N_TILE, ad + 6, b_desc + 6, idesc, 1u);
                                 }
                                 umma_commit(empty_b + 8 * st);   // weight stage free once these MMAs retire
                             }
+                            __syncwarp();
                         }
-                        // plane kd is not needed by later taps of this channel block
-                        umma_commit(empty_a + 8 * ((q_base + kd) % Cfg::A_SLOTS));
                     }
-                    for (int p = KS; p < Cfg::PLANES; ++p) umma_commit(empty_a + 8 * ((q_base + p) % Cfg::A_SLOTS));
-                    q_base += Cfg::PLANES;
+                    // plane kd is not needed by later taps of this channel block
+                    if (elect_one()) umma_commit(empty_a + 8 * ((q_base + kd) % Cfg::A_SLOTS));
+                    __syncwarp();
                 }
-                umma_commit(tmem_full + 8 * as);                 // accumulators complete -> epilogue
+                if (elect_one()) {
+                    for (int p = KS; p < Cfg::PLANES; ++p) umma_commit(empty_a + 8 * ((q_base + p) % Cfg::A_SLOTS));
+                }
+                __syncwarp();
+                q_base += Cfg::PLANES;
             }
+            if (elect_one()) umma_commit(tmem_full + 8 * as);    // accumulators complete -> epilogue
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================

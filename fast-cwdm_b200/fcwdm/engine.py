@@ -89,7 +89,7 @@ class WavUNetEngine:
     def _gn_silu(self, gn, x, N, S, silu=True):
         C = gn.num_channels
         y = self._buf(N * S, C, x.device)
-        stats = torch.empty((N, gn.num_groups, 2), dtype=torch.float64, device=x.device)
+        stats = torch.empty((N, ops.GN_STAT_REPLICAS, gn.num_groups, 2), dtype=torch.float64, device=x.device)
         ops.groupnorm_silu(x, y, stats, self._p32(gn.weight), self._p32(gn.bias), N, S, C, gn.num_groups, gn.eps, silu)
         return y
 

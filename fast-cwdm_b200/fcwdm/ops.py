@@ -9,6 +9,7 @@ from . import native
 from .native import FcwdmError
 
 _VP = ctypes.c_void_p
+GN_STAT_REPLICAS = 16   # FCWDM_GN_STAT_REPLICAS in include/fcwdm.h
 
 
 def _ptr(t):

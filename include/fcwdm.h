@@ -28,6 +28,7 @@ extern "C" {
 #endif
 
 #define FCWDM_VERSION 100 /* 0.1.0 */
+#define FCWDM_GN_STAT_REPLICAS 16
 
 enum fcwdm_dtype { FCWDM_F32 = 0, FCWDM_BF16 = 1 };
 
@@ -129,8 +130,8 @@ int fcwdm_cl_to_planar(const void* src, int64_t src_ld, float* dst, int64_t N, i
 /* ------------------------------------------------------------------------------------------------------
  * K4: GroupNorm32 (+SiLU).  Replaces nn.GroupNorm in fp32 + nn.SiLU (guided_diffusion/nn.py:17-19,
  * wunet.py:186-187,210-211,702-703).  x, y: cl bf16 (N, S voxels, C), voxel stride ld; statistics in fp32
- * per thread, fp64 across blocks.  stats: device double [N][G][2] (sum, sum of squares), zeroed by
- * fcwdm_groupnorm_stats itself.  C % 8 == 0, C % G == 0, (C/G) in {1,2,4,8,...}.
+ * per thread, fp64 across blocks.  stats: device double [N][FCWDM_GN_STAT_REPLICAS][G][2] (sum, sum of squares;
+ * blocks spread their atomics over the replicas, `apply` adds them up), zeroed by fcwdm_groupnorm_stats itself.  C % 8 == 0, C % G == 0, (C/G) in {1,2,4,8,...}.
  * ---------------------------------------------------------------------------------------------------- */
 int fcwdm_groupnorm_stats(const void* x, int64_t ld, double* stats, int64_t N, int64_t S, int64_t C,
                           int64_t G, void* stream);

@@ -99,7 +99,7 @@ def test_groupnorm_silu(C, G, S):
     xb = torch.zeros((N * S, ld), dtype=torch.bfloat16, device="cuda")
     xb[:, :C] = x.reshape(N * S, C).to(torch.bfloat16)
     yb = torch.zeros_like(xb)
-    stats = torch.empty((N, G, 2), dtype=torch.float64, device="cuda")
+    stats = torch.empty((N, 16, G, 2), dtype=torch.float64, device="cuda")
     ops.groupnorm_silu(xb, yb, stats, gamma, beta, N, S, C, G)
     ref = F.silu(F.group_norm(x.permute(0, 2, 1).float(), G, gamma, beta, 1e-5)).permute(0, 2, 1)
     got = yb[:, :C].float().reshape(N, S, C)

@@ -45,7 +45,7 @@ def main():
     S = 112 * 112 * 80
     x = torch.randn((S, 64), device=dev).to(torch.bfloat16)
     y = torch.empty_like(x)
-    stats = torch.empty((1, 32, 2), dtype=torch.float64, device=dev)
+    stats = torch.empty((1, 16, 32, 2), dtype=torch.float64, device=dev)
     g = torch.ones(64, device=dev)
     bb = torch.zeros(64, device=dev)
     from fcwdm import native
