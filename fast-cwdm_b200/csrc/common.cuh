@@ -41,9 +41,36 @@ static inline int num_sms() {
     return n;
 }
 
+// Programmatic dependent launch: every kernel is launched with programmaticStreamSerialization so that its
+// prologue (and its launch latency) overlaps the tail of its predecessor in the stream / captured graph; every
+// kernel calls pdl_prologue() before its first global-memory access, which waits for the full completion (and
+// memory flush) of the predecessor, so ordering semantics are unchanged.  FCWDM_NO_PDL=1 disables the attribute.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 struct __align__(32) float8 {
     float v[8];
 };

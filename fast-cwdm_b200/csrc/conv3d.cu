@@ -153,7 +153,8 @@ struct ConvArgs {
     int n_nt, n_wt, n_ht, n_dt;
     int num_tiles;
     const float* bias;        // [Cout] or null
-    const float* chan_bias;   // [N][Cout] or null
+    const float* chan_bias;   // [N][cb_ld] or null
+    long long cb_ld;
     const __nv_bfloat16* residual;
     long long res_ld;
     __nv_bfloat16* y;
@@ -207,6 +208,7 @@ template <int N_TILE, int TD, int KS>
 __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_b,
                                                               const ConvArgs args) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: let the next kernel start its prologue
     using Cfg = ConvCfg<N_TILE, TD, KS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -251,6 +253,9 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // PDL: barrier init, descriptor prefetch and TMEM allocation above overlapped the predecessor's tail; from here on
+    // this kernel touches global memory, so wait for the predecessor to complete and flush.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         // ================================ A producer: halo planes ================================
@@ -386,7 +391,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
                                     v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
                                 }
                                 if (args.chan_bias != nullptr) {
-                                    const float* cbp = args.chan_bias + (long long)tc.n * args.Cout + co;
+                                    const float* cbp = args.chan_bias + (long long)tc.n * args.cb_ld + co;
                                     const float4 b0 = __ldg(reinterpret_cast<const float4*>(cbp));
                                     const float4 b1 = __ldg(reinterpret_cast<const float4*>(cbp + 4));
                                     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
@@ -421,6 +426,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
 // weights (Cout, Cin, k, k, k) f32 -> [tap][Cout_p][Cin_p] bf16, zero padded
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
                                                            int Cout, int Cin, int Cout_p, int Cin_p, int taps) {
+    pdl_prologue();
     const long long total = (long long)taps * Cout_p * Cin_p;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -477,7 +483,7 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, ConvArgs a,
     FCWDM_REQUIRE(tiles < (1ll << 31), FCWDM_ERR_UNSUPPORTED, "fcwdm_conv3d_fwd: too many tiles");
     a.num_tiles = (int)tiles;
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    conv3d_igemm_kernel<N_TILE, TD, KS><<<grid, 256, Cfg::SMEM_BYTES, st>>>(ma, mb, a);
+    launch_k(conv3d_igemm_kernel<N_TILE, TD, KS>, dim3(grid), dim3(256), Cfg::SMEM_BYTES, st, ma, mb, a);
     FCWDM_CHECK_LAUNCH("fcwdm_conv3d_fwd");
     return FCWDM_OK;
 }
@@ -503,14 +509,14 @@ extern "C" int fcwdm_conv3d_pack_weights(const float* w, void* wp, int64_t Cout,
     const int taps = ksize * ksize * ksize;
     const int cout_p = (int)((Cout + 15) / 16 * 16), cin_p = (int)((Cin + 63) / 64 * 64);
     const long long total = (long long)taps * cout_p * cin_p;
-    pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(pack_weights_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
         w, (__nv_bfloat16*)wp, (int)Cout, (int)Cin, cout_p, cin_p, taps);
     FCWDM_CHECK_LAUNCH("fcwdm_conv3d_pack_weights");
     return FCWDM_OK;
 }
 
 extern "C" int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, const float* bias, const float* chan_bias,
-                                const void* residual, int64_t res_ld, void* y, int64_t y_ld, int64_t N, int64_t D,
+                                int64_t cb_ld, const void* residual, int64_t res_ld, void* y, int64_t y_ld, int64_t N, int64_t D,
                                 int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize, void* stream) {
     FCWDM_REQUIRE(x && wp && y, FCWDM_ERR_INVALID, "fcwdm_conv3d_fwd: null pointer");
     FCWDM_REQUIRE(N >= 0 && D >= 0 && H >= 0 && W >= 0 && Cin > 0 && Cout > 0, FCWDM_ERR_INVALID,
@@ -524,7 +530,8 @@ extern "C" int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, con
     FCWDM_REQUIRE(y_ld >= Cout && y_ld % 8 == 0 && (residual == nullptr || (res_ld >= Cout && res_ld % 8 == 0)),
                   FCWDM_ERR_INVALID, "fcwdm_conv3d_fwd: bad y_ld / res_ld");
     FCWDM_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)wp % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
-                      ((uintptr_t)residual % 16 == 0) && ((uintptr_t)bias % 16 == 0) && ((uintptr_t)chan_bias % 16 == 0),
+                      ((uintptr_t)residual % 16 == 0) && ((uintptr_t)bias % 16 == 0) && ((uintptr_t)chan_bias % 16 == 0) &&
+                      (cb_ld % 4 == 0),
                   FCWDM_ERR_INVALID, "fcwdm_conv3d_fwd: pointers must be 16-byte aligned");
     FCWDM_REQUIRE(D < 32768 && H < 32768 && W < 32768 && N < 32768, FCWDM_ERR_UNSUPPORTED, "fcwdm_conv3d_fwd: dim too large");
     if (N * D * H * W == 0) return FCWDM_OK;
@@ -563,7 +570,7 @@ extern "C" int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, con
     a.N = (int)N; a.D = (int)D; a.H = (int)H; a.W = (int)W;
     a.Cout = (int)Cout;
     a.n_cb = (int)(cin_p / 64);
-    a.bias = bias; a.chan_bias = chan_bias;
+    a.bias = bias; a.chan_bias = chan_bias; a.cb_ld = cb_ld;
     a.residual = (const __nv_bfloat16*)residual; a.res_ld = res_ld;
     a.y = (__nv_bfloat16*)y; a.y_ld = y_ld;
     cudaStream_t st = (cudaStream_t)stream;

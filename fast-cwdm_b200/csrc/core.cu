@@ -1,5 +1,6 @@
 // Library plumbing for the C-ABI: version, thread-local error text, per-device init.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -16,6 +17,15 @@ void set_error(const char* fmt, ...) {
 }
 
 int conv3d_init_device();  // conv3d.cu
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FCWDM_NO_PDL");
+        v = (e != nullptr && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
 
 }  // namespace fcwdm
 

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(256) p_sample_step_kernel(const void* __restri
                                                             const float* __restrict__ coef,
                                                             const int64_t* __restrict__ t, int64_t T, int64_t N,
                                                             int64_t S, int clip, int predict_xstart) {
+    pdl_prologue();
     const int64_t S4 = S >> 2;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * S4) return;
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(256) p_sample_step_scalar(const void* __restri
                                                             const float* __restrict__ coef,
                                                             const int64_t* __restrict__ t, int64_t T, int64_t N,
                                                             int64_t S, int clip, int predict_xstart) {
+    pdl_prologue();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * S) return;
     const int64_t n = idx / S, s = idx % S;
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__
                                                        float* __restrict__ out, const float* __restrict__ coef,
                                                        const int64_t* __restrict__ t, int64_t T, int64_t N,
                                                        int64_t per) {
+    pdl_prologue();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * per) return;
     int64_t ti = t[idx / per];
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(256) sample_to_image_kernel(const float* __res
                                                               const float* __restrict__ cond1,
                                                               float* __restrict__ image, int64_t N, int64_t d,
                                                               int64_t h, int64_t w) {
+    pdl_prologue();
     const int64_t S = d * h * w;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * S) return;
@@ -180,6 +184,7 @@ __global__ void __launch_bounds__(256) sample_to_image_kernel(const float* __res
 // planar f32 (N,C,S) -> cl bf16 (N,S,ld): tile transpose through shared memory
 __global__ void __launch_bounds__(256) planar_to_cl_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                            int64_t dst_ld, int64_t C, int64_t S) {
+    pdl_prologue();
     __shared__ float tile[32][33];
     const int64_t n = blockIdx.z;
     const int64_t s0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
@@ -199,6 +204,7 @@ __global__ void __launch_bounds__(256) planar_to_cl_kernel(const float* __restri
 
 __global__ void __launch_bounds__(256) cl_to_planar_kernel(const __nv_bfloat16* __restrict__ src, int64_t src_ld,
                                                            float* __restrict__ dst, int64_t C, int64_t S) {
+    pdl_prologue();
     __shared__ float tile[32][33];
     const int64_t n = blockIdx.z;
     const int64_t s0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
@@ -243,22 +249,22 @@ extern "C" int fcwdm_p_sample_step(const void* model_out, int64_t mo_cl_ld, cons
         const int64_t total = N * (S / 4);
         const unsigned grid = (unsigned)((total + 255) / 256);
         if (cl)
-            p_sample_step_kernel<true><<<grid, 256, 0, st>>>(model_out, mo_cl_ld, x_t, noise, x_prev, pred_xstart,
+            launch_k(p_sample_step_kernel<true>, dim3(grid), dim3(256), 0, st, model_out, mo_cl_ld, x_t, noise, x_prev, pred_xstart,
                                                             (__nv_bfloat16*)x_prev_cl, xp_cl_ld, coef, t, T, N, S,
                                                             clip_denoised, predict_xstart);
         else
-            p_sample_step_kernel<false><<<grid, 256, 0, st>>>(model_out, 0, x_t, noise, x_prev, pred_xstart,
+            launch_k(p_sample_step_kernel<false>, dim3(grid), dim3(256), 0, st, model_out, 0, x_t, noise, x_prev, pred_xstart,
                                                              (__nv_bfloat16*)x_prev_cl, xp_cl_ld, coef, t, T, N, S,
                                                              clip_denoised, predict_xstart);
     } else {
         const int64_t total = N * S;
         const unsigned grid = (unsigned)((total + 255) / 256);
         if (cl)
-            p_sample_step_scalar<true><<<grid, 256, 0, st>>>(model_out, mo_cl_ld, x_t, noise, x_prev, pred_xstart,
+            launch_k(p_sample_step_scalar<true>, dim3(grid), dim3(256), 0, st, model_out, mo_cl_ld, x_t, noise, x_prev, pred_xstart,
                                                             (__nv_bfloat16*)x_prev_cl, xp_cl_ld, coef, t, T, N, S,
                                                             clip_denoised, predict_xstart);
         else
-            p_sample_step_scalar<false><<<grid, 256, 0, st>>>(model_out, 0, x_t, noise, x_prev, pred_xstart,
+            launch_k(p_sample_step_scalar<false>, dim3(grid), dim3(256), 0, st, model_out, 0, x_t, noise, x_prev, pred_xstart,
                                                              (__nv_bfloat16*)x_prev_cl, xp_cl_ld, coef, t, T, N, S,
                                                              clip_denoised, predict_xstart);
     }
@@ -272,7 +278,7 @@ extern "C" int fcwdm_q_sample(const float* x_start, const float* noise, float* o
     FCWDM_REQUIRE(N >= 0 && per_sample >= 0 && T > 0, FCWDM_ERR_INVALID, "fcwdm_q_sample: bad dimension");
     const int64_t total = N * per_sample;
     if (total == 0) return FCWDM_OK;
-    q_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_start, noise, out, coef, t, T,
+    launch_k(q_sample_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x_start, noise, out, coef, t, T,
                                                                                       N, per_sample);
     FCWDM_CHECK_LAUNCH("fcwdm_q_sample");
     return FCWDM_OK;
@@ -286,7 +292,7 @@ extern "C" int fcwdm_sample_to_image(const float* sample, const float* cond_1, f
                   FCWDM_ERR_INVALID, "fcwdm_sample_to_image: image / cond_1 must be 8-byte aligned");
     const int64_t total = N * d * h * w;
     if (total == 0) return FCWDM_OK;
-    sample_to_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sample, cond_1, image, N,
+    launch_k(sample_to_image_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, sample, cond_1, image, N,
                                                                                              d, h, w);
     FCWDM_CHECK_LAUNCH("fcwdm_sample_to_image");
     return FCWDM_OK;
@@ -299,7 +305,7 @@ extern "C" int fcwdm_planar_to_cl(const float* src, void* dst, int64_t dst_ld, i
                   "fcwdm_planar_to_cl: bad dimension");
     if (N * C * S == 0) return FCWDM_OK;
     dim3 grid((unsigned)((S + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N);
-    planar_to_cl_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, dst_ld, C, S);
+    launch_k(planar_to_cl_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, src, (__nv_bfloat16*)dst, dst_ld, C, S);
     FCWDM_CHECK_LAUNCH("fcwdm_planar_to_cl");
     return FCWDM_OK;
 }
@@ -311,7 +317,7 @@ extern "C" int fcwdm_cl_to_planar(const void* src, int64_t src_ld, float* dst, i
                   "fcwdm_cl_to_planar: bad dimension");
     if (N * C * S == 0) return FCWDM_OK;
     dim3 grid((unsigned)((S + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N);
-    cl_to_planar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, src_ld, dst, C, S);
+    launch_k(cl_to_planar_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)src, src_ld, dst, C, S);
     FCWDM_CHECK_LAUNCH("fcwdm_cl_to_planar");
     return FCWDM_OK;
 }

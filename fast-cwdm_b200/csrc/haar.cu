@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) dwt3d_planar_f32_v8(const float* __restri
                                                            int64_t total, int64_t C, int64_t D, int64_t H,
                                                            int64_t W, int64_t x_sn, int64_t x_sc, int64_t o_sn,
                                                            int64_t o_sc, int64_t o_sb, float lll_scale) {
+    pdl_prologue();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int64_t D2 = D >> 1, H2 = H >> 1, W2 = W >> 1;
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(256) idwt3d_planar_f32_v8(const float* __restr
                                                             int64_t total, int64_t C, int64_t D, int64_t H,
                                                             int64_t W, int64_t b_sn, int64_t b_sc, int64_t b_sb,
                                                             int64_t y_sn, int64_t y_sc, float lll_scale) {
+    pdl_prologue();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int64_t D2 = D >> 1, H2 = H >> 1, W2 = W >> 1;
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(256) dwt3d_planar_bf16_v8(const __nv_bfloat16*
                                                             int64_t C, int64_t D, int64_t H, int64_t W,
                                                             int64_t x_sn, int64_t x_sc, int64_t o_sn, int64_t o_sc,
                                                             int64_t o_sb, float lll_scale) {
+    pdl_prologue();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int64_t D2 = D >> 1, H2 = H >> 1, W2 = W >> 1;
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(256) idwt3d_planar_bf16_v8(const __nv_bfloat16
                                                              int64_t C, int64_t D, int64_t H, int64_t W,
                                                              int64_t b_sn, int64_t b_sc, int64_t b_sb, int64_t y_sn,
                                                              int64_t y_sc, float lll_scale) {
+    pdl_prologue();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int64_t D2 = D >> 1, H2 = H >> 1, W2 = W >> 1;
@@ -207,6 +211,7 @@ __global__ void __launch_bounds__(256) dwt3d_planar_generic(const T* __restrict_
                                                             int64_t total, int64_t C, int64_t D, int64_t H,
                                                             int64_t W, int64_t x_sn, int64_t x_sc, int64_t o_sn,
                                                             int64_t o_sc, int64_t o_sb, float lll_scale) {
+    pdl_prologue();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int64_t D2 = D >> 1, H2 = H >> 1, W2 = W >> 1;
@@ -231,6 +236,7 @@ __global__ void __launch_bounds__(256) idwt3d_planar_generic(const T* __restrict
                                                              int64_t total, int64_t C, int64_t D, int64_t H,
                                                              int64_t W, int64_t b_sn, int64_t b_sc, int64_t b_sb,
                                                              int64_t y_sn, int64_t y_sc, float lll_scale) {
+    pdl_prologue();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int64_t D2 = D >> 1, H2 = H >> 1, W2 = W >> 1;
@@ -256,9 +262,10 @@ __global__ void __launch_bounds__(256) idwt3d_planar_generic(const T* __restrict
 __global__ void __launch_bounds__(256) dwt3d_cl_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld,
                                                        __nv_bfloat16* __restrict__ lll, int64_t lll_ld,
                                                        __nv_bfloat16* __restrict__ hi, int64_t hi_ld, int64_t hi_sb,
-                                                       const float* __restrict__ lll_bias, int64_t total, int64_t D,
-                                                       int64_t H, int64_t W, int64_t C, float lll_scale,
-                                                       float hi_scale) {
+                                                       const float* __restrict__ lll_bias, int64_t bias_ld,
+                                                       int64_t total, int64_t D, int64_t H, int64_t W, int64_t C,
+                                                       float lll_scale, float hi_scale) {
+    pdl_prologue();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int64_t C8 = C >> 3, D2 = D >> 1, H2 = H >> 1, W2 = W >> 1;
@@ -293,8 +300,8 @@ __global__ void __launch_bounds__(256) dwt3d_cl_kernel(const __nv_bfloat16* __re
 #pragma unroll
         for (int c = 0; c < 8; ++c) o[c] = apply_scale(ob[0][c], lll_scale);
         if (lll_bias != nullptr) {
-            const float4 b0 = *reinterpret_cast<const float4*>(lll_bias + n * C + cq * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(lll_bias + n * C + cq * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(lll_bias + n * bias_ld + cq * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(lll_bias + n * bias_ld + cq * 8 + 4);
             o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
             o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
         }
@@ -314,8 +321,10 @@ __global__ void __launch_bounds__(256) dwt3d_cl_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256) idwt3d_cl_kernel(const __nv_bfloat16* __restrict__ lll, int64_t lll_ld,
                                                         const __nv_bfloat16* __restrict__ hi, int64_t hi_ld,
                                                         int64_t hi_sb, __nv_bfloat16* __restrict__ y, int64_t y_ld,
-                                                        const float* __restrict__ bias, int64_t total, int64_t D,
-                                                        int64_t H, int64_t W, int64_t C, float lll_scale) {
+                                                        const float* __restrict__ bias, int64_t bias_ld,
+                                                        int64_t total, int64_t D, int64_t H, int64_t W, int64_t C,
+                                                        float lll_scale) {
+    pdl_prologue();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int64_t C8 = C >> 3, D2 = D >> 1, H2 = H >> 1, W2 = W >> 1;
@@ -334,8 +343,8 @@ __global__ void __launch_bounds__(256) idwt3d_cl_kernel(const __nv_bfloat16* __r
     for (int b = 1; b < 8; ++b) unpack8(ld_stream_u4(hi + (b - 1) * hi_sb + vox * hi_ld + cq * 8), bnd[b]);
     float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (bias != nullptr) {
-        const float4 b0 = *reinterpret_cast<const float4*>(bias + n * C + cq * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(bias + n * C + cq * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + n * bias_ld + cq * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + n * bias_ld + cq * 8 + 4);
         bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w;
         bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
     }
@@ -389,22 +398,22 @@ extern "C" int fcwdm_dwt3d_fwd(const void* x, void* bands, int dtype, int64_t N,
     if (dtype == FCWDM_F32) {
         if (strides_v8 && aligned(x, 32) && aligned(bands, 16)) {
             int64_t total = N * C * (D / 2) * (H / 2) * (W / 8);
-            dwt3d_planar_f32_v8<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(
+            launch_k(dwt3d_planar_f32_v8, dim3((unsigned)((total + threads - 1) / threads)), dim3(threads), 0, st, 
                 (const float*)x, (float*)bands, total, C, D, H, W, x_sn, x_sc, o_sn, o_sc, o_sb, lll_scale);
         } else {
             int64_t total = N * C * (D / 2) * (H / 2) * (W / 2);
-            dwt3d_planar_generic<float><<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(
+            launch_k(dwt3d_planar_generic<float>, dim3((unsigned)((total + threads - 1) / threads)), dim3(threads), 0, st, 
                 (const float*)x, (float*)bands, total, C, D, H, W, x_sn, x_sc, o_sn, o_sc, o_sb, lll_scale);
         }
     } else {
         if (strides_v8 && aligned(x, 16) && aligned(bands, 8)) {
             int64_t total = N * C * (D / 2) * (H / 2) * (W / 8);
-            dwt3d_planar_bf16_v8<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(
+            launch_k(dwt3d_planar_bf16_v8, dim3((unsigned)((total + threads - 1) / threads)), dim3(threads), 0, st, 
                 (const __nv_bfloat16*)x, (__nv_bfloat16*)bands, total, C, D, H, W, x_sn, x_sc, o_sn, o_sc, o_sb,
                 lll_scale);
         } else {
             int64_t total = N * C * (D / 2) * (H / 2) * (W / 2);
-            dwt3d_planar_generic<__nv_bfloat16><<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(
+            launch_k(dwt3d_planar_generic<__nv_bfloat16>, dim3((unsigned)((total + threads - 1) / threads)), dim3(threads), 0, st, 
                 (const __nv_bfloat16*)x, (__nv_bfloat16*)bands, total, C, D, H, W, x_sn, x_sc, o_sn, o_sc, o_sb,
                 lll_scale);
         }
@@ -427,22 +436,22 @@ extern "C" int fcwdm_idwt3d_fwd(const void* bands, void* y, int dtype, int64_t N
     if (dtype == FCWDM_F32) {
         if (strides_v8 && aligned(y, 32) && aligned(bands, 16)) {
             int64_t total = N * C * (D / 2) * (H / 2) * (W / 8);
-            idwt3d_planar_f32_v8<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(
+            launch_k(idwt3d_planar_f32_v8, dim3((unsigned)((total + threads - 1) / threads)), dim3(threads), 0, st, 
                 (const float*)bands, (float*)y, total, C, D, H, W, b_sn, b_sc, b_sb, y_sn, y_sc, lll_scale);
         } else {
             int64_t total = N * C * (D / 2) * (H / 2) * (W / 2);
-            idwt3d_planar_generic<float><<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(
+            launch_k(idwt3d_planar_generic<float>, dim3((unsigned)((total + threads - 1) / threads)), dim3(threads), 0, st, 
                 (const float*)bands, (float*)y, total, C, D, H, W, b_sn, b_sc, b_sb, y_sn, y_sc, lll_scale);
         }
     } else {
         if (strides_v8 && aligned(y, 16) && aligned(bands, 8)) {
             int64_t total = N * C * (D / 2) * (H / 2) * (W / 8);
-            idwt3d_planar_bf16_v8<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(
+            launch_k(idwt3d_planar_bf16_v8, dim3((unsigned)((total + threads - 1) / threads)), dim3(threads), 0, st, 
                 (const __nv_bfloat16*)bands, (__nv_bfloat16*)y, total, C, D, H, W, b_sn, b_sc, b_sb, y_sn, y_sc,
                 lll_scale);
         } else {
             int64_t total = N * C * (D / 2) * (H / 2) * (W / 2);
-            idwt3d_planar_generic<__nv_bfloat16><<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(
+            launch_k(idwt3d_planar_generic<__nv_bfloat16>, dim3((unsigned)((total + threads - 1) / threads)), dim3(threads), 0, st, 
                 (const __nv_bfloat16*)bands, (__nv_bfloat16*)y, total, C, D, H, W, b_sn, b_sc, b_sb, y_sn, y_sc,
                 lll_scale);
         }
@@ -452,38 +461,38 @@ extern "C" int fcwdm_idwt3d_fwd(const void* bands, void* y, int dtype, int64_t N
 }
 
 extern "C" int fcwdm_dwt3d_cl(const void* x, int64_t x_ld, void* lll, int64_t lll_ld, void* hi, int64_t hi_ld,
-                              int64_t hi_sb, const float* lll_bias, int64_t N, int64_t D, int64_t H, int64_t W,
-                              int64_t C, float lll_scale, float hi_scale, void* stream) {
+                              int64_t hi_sb, const float* lll_bias, int64_t bias_ld, int64_t N, int64_t D, int64_t H,
+                              int64_t W, int64_t C, float lll_scale, float hi_scale, void* stream) {
     int rc = check_dims("fcwdm_dwt3d_cl", x, lll, N, C, D, H, W);
     if (rc) return rc;
     FCWDM_REQUIRE(C % 8 == 0 && x_ld % 8 == 0 && lll_ld % 8 == 0 && (hi == nullptr || (hi_ld % 8 == 0 && hi_sb % 8 == 0)),
                   FCWDM_ERR_UNSUPPORTED, "fcwdm_dwt3d_cl: C and strides must be multiples of 8");
-    FCWDM_REQUIRE(aligned(x, 16) && aligned(lll, 16) && aligned(hi, 16) && aligned(lll_bias, 16), FCWDM_ERR_INVALID,
-                  "fcwdm_dwt3d_cl: pointers must be 16-byte aligned");
+    FCWDM_REQUIRE(aligned(x, 16) && aligned(lll, 16) && aligned(hi, 16) && aligned(lll_bias, 16) && bias_ld % 4 == 0,
+                  FCWDM_ERR_INVALID, "fcwdm_dwt3d_cl: pointers must be 16-byte aligned");
     int64_t total = N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
     if (total == 0) return FCWDM_OK;
-    dwt3d_cl_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)lll, lll_ld, (__nv_bfloat16*)hi, hi_ld, hi_sb, lll_bias, total, D,
-        H, W, C, lll_scale, hi_scale);
+    launch_k(dwt3d_cl_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
+        (const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)lll, lll_ld, (__nv_bfloat16*)hi, hi_ld, hi_sb, lll_bias, bias_ld,
+        total, D, H, W, C, lll_scale, hi_scale);
     FCWDM_CHECK_LAUNCH("fcwdm_dwt3d_cl");
     return FCWDM_OK;
 }
 
 extern "C" int fcwdm_idwt3d_cl(const void* lll, int64_t lll_ld, const void* hi, int64_t hi_ld, int64_t hi_sb, void* y,
-                               int64_t y_ld, const float* bias, int64_t N, int64_t D, int64_t H, int64_t W, int64_t C,
-                               float lll_scale, void* stream) {
+                               int64_t y_ld, const float* bias, int64_t bias_ld, int64_t N, int64_t D, int64_t H, int64_t W,
+                               int64_t C, float lll_scale, void* stream) {
     int rc = check_dims("fcwdm_idwt3d_cl", lll, y, N, C, D, H, W);
     if (rc) return rc;
     FCWDM_REQUIRE(hi != nullptr, FCWDM_ERR_INVALID, "fcwdm_idwt3d_cl: null high-band pointer");
     FCWDM_REQUIRE(C % 8 == 0 && y_ld % 8 == 0 && lll_ld % 8 == 0 && hi_ld % 8 == 0 && hi_sb % 8 == 0,
                   FCWDM_ERR_UNSUPPORTED, "fcwdm_idwt3d_cl: C and strides must be multiples of 8");
-    FCWDM_REQUIRE(aligned(y, 16) && aligned(lll, 16) && aligned(hi, 16) && aligned(bias, 16), FCWDM_ERR_INVALID,
-                  "fcwdm_idwt3d_cl: pointers must be 16-byte aligned");
+    FCWDM_REQUIRE(aligned(y, 16) && aligned(lll, 16) && aligned(hi, 16) && aligned(bias, 16) && bias_ld % 4 == 0,
+                  FCWDM_ERR_INVALID, "fcwdm_idwt3d_cl: pointers must be 16-byte aligned");
     int64_t total = N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
     if (total == 0) return FCWDM_OK;
-    idwt3d_cl_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)lll, lll_ld, (const __nv_bfloat16*)hi, hi_ld, hi_sb, (__nv_bfloat16*)y, y_ld, bias, total,
-        D, H, W, C, lll_scale);
+    launch_k(idwt3d_cl_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
+        (const __nv_bfloat16*)lll, lll_ld, (const __nv_bfloat16*)hi, hi_ld, hi_sb, (__nv_bfloat16*)y, y_ld, bias, bias_ld,
+        total, D, H, W, C, lll_scale);
     FCWDM_CHECK_LAUNCH("fcwdm_idwt3d_cl");
     return FCWDM_OK;
 }

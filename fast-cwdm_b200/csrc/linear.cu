@@ -7,6 +7,7 @@ namespace fcwdm {
 
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int64_t N, int dim,
                                           float max_period) {
+    pdl_prologue();
     const int half = dim / 2;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * dim) return;
@@ -28,6 +29,7 @@ __device__ __forceinline__ float act(float v, int kind) { return kind == 1 ? v /
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                      const float* __restrict__ b, float* __restrict__ y, int64_t N,
                                                      int64_t K, int64_t M, int act_in, int act_out) {
+    pdl_prologue();
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= N * M) return;
@@ -49,7 +51,7 @@ extern "C" int fcwdm_timestep_embedding(const int64_t* t, float* out, int64_t N,
     FCWDM_REQUIRE(N >= 0 && dim > 0 && max_period > 0.f, FCWDM_ERR_INVALID, "fcwdm_timestep_embedding: bad argument");
     if (N == 0) return FCWDM_OK;
     const int64_t total = N * dim;
-    timestep_embedding_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(t, out, N, (int)dim,
+    launch_k(timestep_embedding_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, t, out, N, (int)dim,
                                                                                                 max_period);
     FCWDM_CHECK_LAUNCH("fcwdm_timestep_embedding");
     return FCWDM_OK;
@@ -63,7 +65,7 @@ extern "C" int fcwdm_linear(const float* x, const float* W, const float* b, floa
                   "fcwdm_linear: activation must be 0 (identity) or 1 (SiLU)");
     if (N * M == 0) return FCWDM_OK;
     const int64_t warps = N * M;
-    linear_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, W, b, y, N, K, M, act_in,
+    launch_k(linear_kernel, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, W, b, y, N, K, M, act_in,
                                                                                          act_out);
     FCWDM_CHECK_LAUNCH("fcwdm_linear");
     return FCWDM_OK;

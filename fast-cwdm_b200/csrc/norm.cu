@@ -16,6 +16,7 @@ constexpr int kStatReplicas = 16;
 
 __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld,
                                                                 double* __restrict__ stats, int64_t S, int C, int G) {
+    pdl_prologue();
     extern __shared__ float sm[];  // [16][kNormThreads] per-thread partials, then [2][C] per-channel sums
     float* part = sm;
     float* chs = sm + 16 * kNormThreads;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __nv_bfloa
                                                                 const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, int64_t S, int C, int G,
                                                                 float eps) {
+    pdl_prologue();
     extern __shared__ float sm[];  // [2][C]: scale, shift
     const int n = blockIdx.y;
     const int cpg = C / G;
@@ -189,7 +191,7 @@ extern "C" int fcwdm_groupnorm_stats(const void* x, int64_t ld, double* stats, i
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     dim3 grid((unsigned)blocks, (unsigned)N);
-    gn_stats_kernel<<<grid, kNormThreads, (16 * kNormThreads + 2 * C) * sizeof(float), st>>>((const __nv_bfloat16*)x, ld, stats, S, (int)C,
+    launch_k(gn_stats_kernel, dim3(grid), dim3(kNormThreads), (16 * kNormThreads + 2 * C) * sizeof(float), st, (const __nv_bfloat16*)x, ld, stats, S, (int)C,
                                                                         (int)G);
     FCWDM_CHECK_LAUNCH("fcwdm_groupnorm_stats");
     return FCWDM_OK;
@@ -212,10 +214,10 @@ extern "C" int fcwdm_groupnorm_apply(const void* x, int64_t x_ld, void* y, int64
     dim3 grid((unsigned)blocks, (unsigned)N);
     cudaStream_t st = (cudaStream_t)stream;
     if (silu)
-        gn_apply_kernel<true><<<grid, kNormThreads, 2 * C * sizeof(float), st>>>(
+        launch_k(gn_apply_kernel<true>, dim3(grid), dim3(kNormThreads), 2 * C * sizeof(float), st, 
             (const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)y, y_ld, stats, gamma, beta, S, (int)C, (int)G, eps);
     else
-        gn_apply_kernel<false><<<grid, kNormThreads, 2 * C * sizeof(float), st>>>(
+        launch_k(gn_apply_kernel<false>, dim3(grid), dim3(kNormThreads), 2 * C * sizeof(float), st, 
             (const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)y, y_ld, stats, gamma, beta, S, (int)C, (int)G, eps);
     FCWDM_CHECK_LAUNCH("fcwdm_groupnorm_apply");
     return FCWDM_OK;

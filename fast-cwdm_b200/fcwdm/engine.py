@@ -59,6 +59,23 @@ class WavUNetEngine:
                 pk.bias = mod.bias.detach().float().contiguous() if mod.bias is not None else None
                 pk.cout, pk.cin, pk.k = mod.out_channels, mod.in_channels, k
                 self._conv[id(mod)] = pk
+        # all per-ResBlock timestep projections Linear(SiLU(emb)) (wunet.py:203-206,250) as ONE dense layer:
+        # rows of W_cat are the concatenated emb_layers[1] weights; a block reads its column slice of the result
+        from guided_diffusion.wunet import ResBlock
+        self._emb_off, ws, bs, off = {}, [], [], 0
+        for mod in self.model.modules():
+            if isinstance(mod, ResBlock) and id(mod) not in self._emb_off:
+                lin = mod.emb_layers[1]
+                self._emb_off[id(mod)] = (off, lin.out_features)
+                ws.append(lin.weight.detach().float())
+                bs.append(lin.bias.detach().float())
+                off += (lin.out_features + 3) // 4 * 4      # keep every slice 16-byte aligned
+                if off != self._emb_off[id(mod)][0] + lin.out_features:
+                    pad = off - self._emb_off[id(mod)][0] - lin.out_features
+                    ws.append(torch.zeros((pad, lin.in_features), device=device))
+                    bs.append(torch.zeros((pad,), device=device))
+        self._emb_w = torch.cat(ws, dim=0).contiguous()
+        self._emb_b = torch.cat(bs, dim=0).contiguous()
         self._sig = sig
         self._device = device
 
@@ -93,11 +110,14 @@ class WavUNetEngine:
         ops.groupnorm_silu(x, y, stats, self._p32(gn.weight), self._p32(gn.bias), N, S, C, gn.num_groups, gn.eps, silu)
         return y
 
-    def _emb_out(self, blk, emb):
-        lin = blk.emb_layers[1]
-        out = torch.empty((emb.shape[0], lin.out_features), dtype=torch.float32, device=emb.device)
-        ops.linear(emb, self._p32(lin.weight), self._p32(lin.bias), out, act_in=1, act_out=0)   # Linear(SiLU(emb))
+    def _emb_all(self, emb):
+        out = torch.empty((emb.shape[0], self._emb_w.shape[0]), dtype=torch.float32, device=emb.device)
+        ops.linear(emb, self._emb_w, self._emb_b, out, act_in=1, act_out=0)                      # Linear(SiLU(emb))
         return out
+
+    def _emb_out(self, blk, emb_all):
+        off, n = self._emb_off[id(blk)]
+        return emb_all[:, off:off + n]          # strided view: the kernels take the row stride (bias_ld / cb_ld)
 
     def _resblock(self, blk, x, skip, emb, N, dims):
         """ResBlock.forward (reference wunet.py:223-269).  Returns (out, skip_out, dims_out)."""
@@ -162,7 +182,7 @@ class WavUNetEngine:
             if dim % (2 ** levels):
                 raise FcwdmError(f"spatial size {tuple(dims)} is not divisible by 2^{levels} (one Haar level per "
                                  f"channel_mult entry; the reference fails the same way, SURVEY.md fact 3)")
-        emb = self.time_embedding(t)
+        emb = self._emb_all(self.time_embedding(t))
         hs = []
         pyramid, pyr_dims, pyr_c = x_cl, tuple(dims), m.in_channels
         h, hdims = x_cl, tuple(dims)

@@ -23,8 +23,8 @@ PROTOTYPES = {
     "fcwdm_init": (_c_int, [_c_int]),
     "fcwdm_dwt3d_fwd": (_c_int, [_c_p, _c_p, _c_int] + [_c_i64] * 10 + [_c_f, _c_p]),
     "fcwdm_idwt3d_fwd": (_c_int, [_c_p, _c_p, _c_int] + [_c_i64] * 10 + [_c_f, _c_p]),
-    "fcwdm_dwt3d_cl": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_p] + [_c_i64] * 5 + [_c_f, _c_f, _c_p]),
-    "fcwdm_idwt3d_cl": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_p, _c_i64, _c_p] + [_c_i64] * 5 + [_c_f, _c_p]),
+    "fcwdm_dwt3d_cl": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_p] + [_c_i64] * 6 + [_c_f, _c_f, _c_p]),
+    "fcwdm_idwt3d_cl": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_p, _c_i64, _c_p] + [_c_i64] * 6 + [_c_f, _c_p]),
     "fcwdm_p_sample_step": (_c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_p] + [_c_i64] * 5
                             + [_c_int, _c_int, _c_p]),
     "fcwdm_q_sample": (_c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_p]),
@@ -38,7 +38,7 @@ PROTOTYPES = {
     "fcwdm_linear": (_c_int, [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_p]),
     "fcwdm_conv3d_packed_elems": (_c_i64, [_c_i64, _c_i64, _c_int]),
     "fcwdm_conv3d_pack_weights": (_c_int, [_c_p, _c_p, _c_i64, _c_i64, _c_int, _c_p]),
-    "fcwdm_conv3d_fwd": (_c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64] + [_c_i64] * 6
+    "fcwdm_conv3d_fwd": (_c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64] + [_c_i64] * 6
                          + [_c_int, _c_p]),
 }
 

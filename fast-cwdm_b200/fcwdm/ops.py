@@ -149,15 +149,15 @@ def dwt3d_cl(x, dims, C, lll, hi, lll_bias=None, lll_scale=1.0 / 3.0, hi_scale=1
     with _on(x.device) as st:
         native.call("fcwdm_dwt3d_cl", _ptr(x), x.stride(0), _ptr(lll), lll.stride(0), _ptr(hi),
                     hi.stride(-2) if hi is not None else 0,
-                    (hi_sb if hi_sb is not None else (hi.stride(0) if hi is not None else 0)), _ptr(lll_bias), N, D, H, W,
-                    C, float(lll_scale), float(hi_scale), st)
+                    (hi_sb if hi_sb is not None else (hi.stride(0) if hi is not None else 0)), _ptr(lll_bias),
+                    lll_bias.stride(0) if lll_bias is not None else 0, N, D, H, W, C, float(lll_scale), float(hi_scale), st)
 
 
 def idwt3d_cl(lll, hi, dims_out, C, y, bias=None, lll_scale=3.0):
     N, D, H, W = dims_out
     with _on(y.device) as st:
         native.call("fcwdm_idwt3d_cl", _ptr(lll), lll.stride(0), _ptr(hi), hi.stride(-2), hi.stride(0), _ptr(y),
-                    y.stride(0), _ptr(bias), N, D, H, W, C, float(lll_scale), st)
+                    y.stride(0), _ptr(bias), bias.stride(0) if bias is not None else 0, N, D, H, W, C, float(lll_scale), st)
 
 
 def planar_to_cl(src, dst, C):
@@ -214,7 +214,8 @@ def conv3d_cl(x, wp, bias, y, dims, cin, cout, k, chan_bias=None, residual=None)
     """x, y, residual: cl bf16 buffers (voxels, ld).  dims = (N, D, H, W)."""
     N, D, H, W = dims
     with _on(x.device) as st:
-        native.call("fcwdm_conv3d_fwd", _ptr(x), x.stride(0), _ptr(wp), _ptr(bias), _ptr(chan_bias), _ptr(residual),
+        native.call("fcwdm_conv3d_fwd", _ptr(x), x.stride(0), _ptr(wp), _ptr(bias), _ptr(chan_bias),
+                    chan_bias.stride(0) if chan_bias is not None else 0, _ptr(residual),
                     residual.stride(0) if residual is not None else 0, _ptr(y), y.stride(0), N, D, H, W, cin, cout, k, st)
 
 

@@ -73,20 +73,20 @@ int fcwdm_idwt3d_fwd(const void* bands, void* y, int dtype, int64_t N, int64_t C
  * Channels-last bf16 DWT / IDWT used inside the denoiser (Downsample / Upsample / WaveletDownsample,
  * guided_diffusion/wunet.py:40-145).
  * x: (N, D, H, W, C) bf16, voxel stride x_ld (>= C).  C % 8 == 0.
- * dwt: LLL -> lll[voxel*lll_ld + c] * lll_scale (+ lll_bias[n*C + c] if non-null: the timestep-embedding
- *      add that follows the down-sampling, wunet.py:262);
+ * dwt: LLL -> lll[voxel*lll_ld + c] * lll_scale (+ lll_bias[n*bias_ld + c] if non-null: the timestep-embedding
+ *      add that follows the down-sampling, wunet.py:262; bias_ld = row stride of the per-sample bias matrix);
  *      band b=1..7 -> hi[(b-1)*hi_sb + voxel*hi_ld + c] * hi_scale; hi == NULL skips them (x_upd branch,
  *      wunet.py:241, which discards the 7 bands).
  *      WaveletDownsample's cat(...)/3 (wunet.py:143-144): lll = buf, hi = buf + C, hi_sb = C,
  *      lll_ld = hi_ld = 8*C, both scales 1/3.
- * idwt: y[voxel*y_ld + c] = IDWT(lll*lll_scale, hi...) (+ bias[n*C + c]).
+ * idwt: y[voxel*y_ld + c] = IDWT(lll*lll_scale, hi...) (+ bias[n*bias_ld + c]).
  * ---------------------------------------------------------------------------------------------------- */
 int fcwdm_dwt3d_cl(const void* x, int64_t x_ld, void* lll, int64_t lll_ld, void* hi, int64_t hi_ld,
-                   int64_t hi_sb, const float* lll_bias, int64_t N, int64_t D, int64_t H, int64_t W,
-                   int64_t C, float lll_scale, float hi_scale, void* stream);
+                   int64_t hi_sb, const float* lll_bias, int64_t bias_ld, int64_t N, int64_t D, int64_t H,
+                   int64_t W, int64_t C, float lll_scale, float hi_scale, void* stream);
 int fcwdm_idwt3d_cl(const void* lll, int64_t lll_ld, const void* hi, int64_t hi_ld, int64_t hi_sb,
-                    void* y, int64_t y_ld, const float* bias, int64_t N, int64_t D, int64_t H, int64_t W,
-                    int64_t C, float lll_scale, void* stream);
+                    void* y, int64_t y_ld, const float* bias, int64_t bias_ld, int64_t N, int64_t D, int64_t H,
+                    int64_t W, int64_t C, float lll_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * K3: fused reverse-diffusion step.  Replaces process_xstart + q_posterior_mean_variance + the sampling
@@ -159,13 +159,13 @@ int fcwdm_linear(const float* x, const float* W, const float* b, float* y, int64
  *   fcwdm_conv3d_packed_elems).
  * fcwdm_conv3d_fwd: x cl bf16 (N,D,H,W, x_ld >= Cin_p channels readable; channels Cin..Cin_p-1 must be
  *   finite, they meet zero weights), y cl bf16 (N,D,H,W,Cout) with voxel stride y_ld;
- *   y = conv(x, w) + bias[c] (+ chan_bias[n*Cout + c]: the timestep-embedding add, wunet.py:262)
+ *   y = conv(x, w) + bias[c] (+ chan_bias[n*cb_ld + c]: the timestep-embedding add, wunet.py:262)
  *       (+ residual[voxel*res_ld + c]: the ResBlock skip add, wunet.py:266, or `input_pyramid + h`, :759).
  * ---------------------------------------------------------------------------------------------------- */
 int64_t fcwdm_conv3d_packed_elems(int64_t Cout, int64_t Cin, int ksize);
 int fcwdm_conv3d_pack_weights(const float* w, void* wp, int64_t Cout, int64_t Cin, int ksize, void* stream);
 int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, const float* bias, const float* chan_bias,
-                     const void* residual, int64_t res_ld, void* y, int64_t y_ld, int64_t N, int64_t D,
+                     int64_t cb_ld, const void* residual, int64_t res_ld, void* y, int64_t y_ld, int64_t N, int64_t D,
                      int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize, void* stream);
 
 #ifdef __cplusplus
