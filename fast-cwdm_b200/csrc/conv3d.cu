@@ -159,6 +159,8 @@ struct ConvArgs {
     long long res_ld;
     __nv_bfloat16* y;
     long long y_ld;
+    double* gn_stats;   // [N][FCWDM_GN_STAT_REPLICAS][gn_groups][2] (pre-zeroed by the caller) or null
+    int gn_cpg, gn_groups;
 };
 
 template <int N_TILE, int TD, int KS>
@@ -172,14 +174,14 @@ struct ConvCfg {
     static constexpr int PLANES = TD + 2 * PAD;
     static constexpr int B_BYTES = N_TILE * 128;
     static constexpr int B_STAGES = (N_TILE >= 128) ? 3 : 4;
-    static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;  // 1 KB alignment slack + 1 KB barriers
+    static constexpr int SMEM_BUDGET = 227 * 1024 - 3072;  // 1 KB alignment slack + 1 KB barriers + 1 KB GN statistics
     static constexpr int A_SLOTS_RAW = (SMEM_BUDGET - B_STAGES * B_BYTES) / SLOT_BYTES;
     static constexpr int A_SLOTS = A_SLOTS_RAW > 12 ? 12 : A_SLOTS_RAW;
     static constexpr int ACC_COLS = TD * N_TILE;
     static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
     static constexpr int TMEM_RAW = ACC_STAGES * ACC_COLS;
     static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : TMEM_RAW <= 64 ? 64 : TMEM_RAW <= 128 ? 128 : TMEM_RAW <= 256 ? 256 : 512;
-    static constexpr int SMEM_BYTES = 1024 + A_SLOTS * SLOT_BYTES + B_STAGES * B_BYTES + 1024;
+    static constexpr int SMEM_BYTES = 1024 + A_SLOTS * SLOT_BYTES + B_STAGES * B_BYTES + 2048;
     static constexpr int CHUNK = 16;                     // accumulator columns per tcgen05.ld
     static_assert(A_SLOTS >= TD + 1, "not enough plane slots");
     static_assert(ACC_COLS <= 512, "accumulators exceed tensor memory");
@@ -204,6 +206,63 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const ConvArgs& a, in
     return t;
 }
 
+// ---- fused GroupNorm statistics (epilogue) ----------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// vr: the 8 consecutive output channels [co, co+8) of this lane's voxel; CPG channels per group (CPG <= 4 here)
+template <int CPG>
+__device__ __forceinline__ void gn_accumulate(const float* vr, float* my_stat, int co, int lane) {
+#pragma unroll
+    for (int g = 0; g < 8 / CPG; ++g) {
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int e = 0; e < CPG; ++e) {
+            s += vr[g * CPG + e];
+            q = fmaf(vr[g * CPG + e], vr[g * CPG + e], q);
+        }
+        s = warp_sum(s);
+        q = warp_sum(q);
+        if (lane == 0) {
+            const int grp = co / CPG + g;
+            my_stat[2 * grp] += s;
+            my_stat[2 * grp + 1] += q;
+        }
+    }
+}
+// CPG >= 8: the whole 8-channel run belongs to one group
+__device__ __forceinline__ void gn_accumulate_wide(const float* vr, float* my_stat, int grp, int lane) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        s += vr[e];
+        q = fmaf(vr[e], vr[e], q);
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0) {
+        my_stat[2 * grp] += s;
+        my_stat[2 * grp + 1] += q;
+    }
+}
+// 4 epilogue warps -> one fp64 atomic per (group, component); blocks spread over FCWDM_GN_STAT_REPLICAS replicas
+__device__ __forceinline__ void flush_gn_stats(float* wstat, const ConvArgs& args, int n, int ew, int lane) {
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int e = ew * 32 + lane;
+    if (e < 2 * args.gn_groups) {
+        const double v = (double)wstat[e] + (double)wstat[64 + e] + (double)wstat[128 + e] + (double)wstat[192 + e];
+        double* dst = args.gn_stats +
+                      (((long long)n * FCWDM_GN_STAT_REPLICAS + (blockIdx.x % FCWDM_GN_STAT_REPLICAS)) * args.gn_groups) * 2;
+        atomicAdd(dst + e, v);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    wstat[ew * 64 + lane] = 0.f;
+    wstat[ew * 64 + 32 + lane] = 0.f;
+    __syncwarp();
+}
+
 template <int N_TILE, int TD, int KS>
 __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_b,
@@ -224,6 +283,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
     const uint32_t tmem_empty = tmem_full + 8 * Cfg::ACC_STAGES;
     const uint32_t tmem_slot = tmem_empty + 8 * Cfg::ACC_STAGES;   // 4 B: TMEM base address
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    float* wstat = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));   // [4 warps][32 groups][2]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -357,9 +417,23 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
         const int ew = warp - 4;                  // == warp % 4: TMEM lane quarter this warp may access
         const int row = ew * 32 + lane;           // accumulator row = voxel within the 16 x 8 tile
         const int hh = row >> 3, ww = row & 7;
+        // fused GroupNorm statistics of the OUTPUT tensor (consumed by the next GroupNorm): per-warp fp32
+        // (sum, sumsq) per group in shared memory, flushed with fp64 atomics when the sample index changes / at exit
+        const bool want_stats = args.gn_stats != nullptr;
+        float* my_stat = wstat + ew * 64;
+        if (want_stats) {
+            my_stat[lane] = 0.f;
+            my_stat[lane + 32] = 0.f;
+            __syncwarp();
+        }
+        int cur_n = -1;
         uint32_t acc_it = 0;
         for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++acc_it) {
             const TileCoord tc = decode_tile(tile, args, TD, N_TILE);
+            if (want_stats && tc.n != cur_n) {
+                if (cur_n >= 0) flush_gn_stats(wstat, args, cur_n, ew, lane);
+                cur_n = tc.n;
+            }
             const uint32_t as = acc_it % Cfg::ACC_STAGES, aph = (acc_it / Cfg::ACC_STAGES) & 1;
             mbar_wait(tmem_full + 8 * as, aph);
             tc_fence_after();
@@ -376,34 +450,47 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
                     uint32_t acc[16];
                     tmem_ld_x16(taddr + c0, acc);
                     tmem_ld_wait();
-                    if (ok) {
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            const int co = tc.n0 + c0 + g * 8;
-                            if (co < args.Cout) {
-                                float v[8];
+                    for (int g = 0; g < 2; ++g) {
+                        const int co = tc.n0 + c0 + g * 8;
+                        if (co < args.Cout) {                                   // warp-uniform
+                            float v[8];
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[g * 8 + e]);
-                                if (args.bias != nullptr) {
-                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + co));
-                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + co + 4));
-                                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                                }
-                                if (args.chan_bias != nullptr) {
-                                    const float* cbp = args.chan_bias + (long long)tc.n * args.cb_ld + co;
-                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(cbp));
-                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(cbp + 4));
-                                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                                }
-                                if (args.residual != nullptr) {
-                                    float rr[8];
-                                    unpack8(*reinterpret_cast<const uint4*>(args.residual + vox * args.res_ld + co), rr);
+                            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[g * 8 + e]);
+                            if (args.bias != nullptr) {
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + co));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + co + 4));
+                                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                            }
+                            if (args.chan_bias != nullptr) {
+                                const float* cbp = args.chan_bias + (long long)tc.n * args.cb_ld + co;
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(cbp));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(cbp + 4));
+                                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                            }
+                            if (ok && args.residual != nullptr) {
+                                float rr[8];
+                                unpack8(*reinterpret_cast<const uint4*>(args.residual + vox * args.res_ld + co), rr);
 #pragma unroll
-                                    for (int e = 0; e < 8; ++e) v[e] += rr[e];
+                                for (int e = 0; e < 8; ++e) v[e] += rr[e];
+                            }
+                            const uint4 packed = pack8(v);
+                            if (ok) *reinterpret_cast<uint4*>(args.y + vox * args.y_ld + co) = packed;
+                            if (want_stats) {                                    // warp-uniform
+                                float vr[8];                                     // statistics of the STORED (bf16) values
+                                unpack8(packed, vr);
+                                if (!ok) {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) vr[e] = 0.f;
                                 }
-                                *reinterpret_cast<uint4*>(args.y + vox * args.y_ld + co) = pack8(v);
+                                switch (args.gn_cpg) {
+                                    case 1: gn_accumulate<1>(vr, my_stat, co, lane); break;
+                                    case 2: gn_accumulate<2>(vr, my_stat, co, lane); break;
+                                    case 4: gn_accumulate<4>(vr, my_stat, co, lane); break;
+                                    default: gn_accumulate_wide(vr, my_stat, co / args.gn_cpg, lane); break;
+                                }
                             }
                         }
                     }
@@ -413,6 +500,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + 8 * as);
         }
+        if (want_stats && cur_n >= 0) flush_gn_stats(wstat, args, cur_n, ew, lane);
     }
 
     tc_fence_before();
@@ -516,8 +604,9 @@ extern "C" int fcwdm_conv3d_pack_weights(const float* w, void* wp, int64_t Cout,
 }
 
 extern "C" int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, const float* bias, const float* chan_bias,
-                                int64_t cb_ld, const void* residual, int64_t res_ld, void* y, int64_t y_ld, int64_t N, int64_t D,
-                                int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize, void* stream) {
+                                int64_t cb_ld, const void* residual, int64_t res_ld, void* y, int64_t y_ld, double* gn_stats,
+                                int64_t gn_groups, int64_t N, int64_t D, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                                int ksize, void* stream) {
     FCWDM_REQUIRE(x && wp && y, FCWDM_ERR_INVALID, "fcwdm_conv3d_fwd: null pointer");
     FCWDM_REQUIRE(N >= 0 && D >= 0 && H >= 0 && W >= 0 && Cin > 0 && Cout > 0, FCWDM_ERR_INVALID,
                   "fcwdm_conv3d_fwd: bad dimension");
@@ -534,6 +623,13 @@ extern "C" int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, con
                       (cb_ld % 4 == 0),
                   FCWDM_ERR_INVALID, "fcwdm_conv3d_fwd: pointers must be 16-byte aligned");
     FCWDM_REQUIRE(D < 32768 && H < 32768 && W < 32768 && N < 32768, FCWDM_ERR_UNSUPPORTED, "fcwdm_conv3d_fwd: dim too large");
+    if (gn_stats != nullptr) {
+        FCWDM_REQUIRE(gn_groups > 0 && gn_groups <= 32 && Cout % gn_groups == 0, FCWDM_ERR_UNSUPPORTED,
+                      "fcwdm_conv3d_fwd: fused GroupNorm statistics need 1 <= groups <= 32 dividing C_out");
+        const int64_t cpg = Cout / gn_groups;
+        FCWDM_REQUIRE(cpg == 1 || cpg == 2 || cpg == 4 || cpg % 8 == 0, FCWDM_ERR_UNSUPPORTED,
+                      "fcwdm_conv3d_fwd: fused GroupNorm statistics need channels/group in {1,2,4,8k}");
+    }
     if (N * D * H * W == 0) return FCWDM_OK;
     if (g_encode == nullptr) {
         int dev = 0;
@@ -573,6 +669,9 @@ extern "C" int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, con
     a.bias = bias; a.chan_bias = chan_bias; a.cb_ld = cb_ld;
     a.residual = (const __nv_bfloat16*)residual; a.res_ld = res_ld;
     a.y = (__nv_bfloat16*)y; a.y_ld = y_ld;
+    a.gn_stats = gn_stats;
+    a.gn_groups = gn_stats ? (int)gn_groups : 0;
+    a.gn_cpg = gn_stats ? (int)(Cout / gn_groups) : 0;
     cudaStream_t st = (cudaStream_t)stream;
 
     // tile-shape choice: prefer deep (TD) and wide (N_TILE) tiles for operand reuse, unless that leaves SMs idle

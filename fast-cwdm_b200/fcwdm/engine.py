@@ -34,6 +34,11 @@ class WavUNetEngine:
         self._conv = {}
         self._f32 = {}
         self._device = None
+        self._stats = {}
+        self._arena = None
+        self._arena_pos = 0
+        import os
+        self.fuse_stats = os.environ.get("FCWDM_NO_FUSED_STATS", "0") != "1"
 
     # ------------------------------------------------------------------ weights
     def _signature(self):
@@ -95,19 +100,42 @@ class WavUNetEngine:
             return torch.empty((rows, ld), dtype=torch.bfloat16, device=device)
         return torch.zeros((rows, ld), dtype=torch.bfloat16, device=device)   # pad channels feed zero weights
 
-    def _conv3d(self, mod, x, N, dims, chan_bias=None, residual=None, out_ld=None):
+    def _conv3d(self, mod, x, N, dims, chan_bias=None, residual=None, out_ld=None, stats_groups=0):
+        """stats_groups > 0: the conv epilogue also produces the GroupNorm statistics of its output (kept in
+        self._stats under the output buffer's id until the consuming GroupNorm picks them up)."""
         pk = self._conv[id(mod)]
         rows = N * dims[0] * dims[1] * dims[2]
         y = self._buf(rows, pk.cout, x.device, out_ld)
+        stats = None
+        cpg = pk.cout // stats_groups if stats_groups and pk.cout % stats_groups == 0 else 0
+        if self.fuse_stats and stats_groups and stats_groups <= 32 and (cpg in (1, 2, 4) or (cpg and cpg % 8 == 0)):
+            stats = self._stats_slot(N, stats_groups, x.device)
+            self._stats[id(y)] = (stats, stats_groups, y)     # holding y keeps its id unique until consumed
         ops.conv3d_cl(x, pk.wp, pk.bias, y, (N,) + tuple(dims), pk.cin, pk.cout, pk.k, chan_bias=chan_bias,
-                      residual=residual)
+                      residual=residual, gn_stats=stats, gn_groups=stats_groups if stats is not None else 0)
         return y
+
+    def _stats_slot(self, N, G, device):
+        """Slice of the per-forward statistics arena (zeroed by ONE memset at the start of forward_cl)."""
+        n = N * ops.GN_STAT_REPLICAS * G * 2
+        if self._arena is None or self._arena_pos + n > self._arena.numel():
+            self._arena = torch.zeros(max(n, 1 << 18), dtype=torch.float64, device=device)   # overflow: fresh arena
+            self._arena_pos = 0
+        out = self._arena[self._arena_pos:self._arena_pos + n].view(N, ops.GN_STAT_REPLICAS, G, 2)
+        self._arena_pos += n
+        return out
 
     def _gn_silu(self, gn, x, N, S, silu=True):
         C = gn.num_channels
         y = self._buf(N * S, C, x.device)
-        stats = torch.empty((N, ops.GN_STAT_REPLICAS, gn.num_groups, 2), dtype=torch.float64, device=x.device)
-        ops.groupnorm_silu(x, y, stats, self._p32(gn.weight), self._p32(gn.bias), N, S, C, gn.num_groups, gn.eps, silu)
+        pre = self._stats.pop(id(x), None)
+        if pre is not None and pre[1] == gn.num_groups and pre[2] is x:
+            stats, have = pre[0], True
+        else:
+            stats, have = torch.empty((N, ops.GN_STAT_REPLICAS, gn.num_groups, 2), dtype=torch.float64,
+                                      device=x.device), False
+        ops.groupnorm_silu(x, y, stats, self._p32(gn.weight), self._p32(gn.bias), N, S, C, gn.num_groups, gn.eps, silu,
+                           have_stats=have)
         return y
 
     def _emb_all(self, emb):
@@ -151,11 +179,13 @@ class WavUNetEngine:
             ops.idwt3d_cl(x, skip, (N,) + d2, cin, xu, bias=None, lll_scale=3.0)          # IDWT(3x, skip)
             x, dims, S, skip_out = xu, d2, s2, None
         else:
-            h = self._conv3d(blk.in_layers[2], a, N, dims, chan_bias=emb_out)            # conv + emb (:262)
+            h = self._conv3d(blk.in_layers[2], a, N, dims, chan_bias=emb_out,             # conv + emb (:262)
+                             stats_groups=blk.out_layers[0].num_groups)
         b = self._gn_silu(blk.out_layers[0], h, N, S)
         if isinstance(blk.skip_connection, torch.nn.Conv3d):
             x = self._conv3d(blk.skip_connection, x, N, dims)
-        out = self._conv3d(blk.out_layers[3], b, N, dims, residual=x)                    # skip(x) + h (:266)
+        out = self._conv3d(blk.out_layers[3], b, N, dims, residual=x,                     # skip(x) + h (:266)
+                           stats_groups=self.model.num_groups)
         return out, skip_out, dims
 
     # ------------------------------------------------------------------ whole network
@@ -182,6 +212,9 @@ class WavUNetEngine:
             if dim % (2 ** levels):
                 raise FcwdmError(f"spatial size {tuple(dims)} is not divisible by 2^{levels} (one Haar level per "
                                  f"channel_mult entry; the reference fails the same way, SURVEY.md fact 3)")
+        self._stats.clear()
+        self._arena = torch.zeros(1 << 18, dtype=torch.float64, device=x_cl.device)   # one memset per forward
+        self._arena_pos = 0
         emb = self._emb_all(self.time_embedding(t))
         hs = []
         pyramid, pyr_dims, pyr_c = x_cl, tuple(dims), m.in_channels
@@ -195,13 +228,13 @@ class WavUNetEngine:
                 cat = self._buf(N * s2, 8 * pyr_c, x_cl.device)
                 ops.dwt3d_cl(pyramid, (N,) + pyr_dims, pyr_c, cat[:, :pyr_c], cat[:, pyr_c:], lll_scale=1.0 / 3.0,
                              hi_scale=1.0 / 3.0, hi_sb=pyr_c)
-                pyramid = self._conv3d(first.conv, cat, N, d2, residual=h)
+                pyramid = self._conv3d(first.conv, cat, N, d2, residual=h, stats_groups=m.num_groups)
                 pyr_dims, pyr_c = d2, first.out_ch
                 h = pyramid
                 continue
             skip = None
             if isinstance(first, torch.nn.Conv3d):
-                h = self._conv3d(first, h, N, hdims)
+                h = self._conv3d(first, h, N, hdims, stats_groups=m.num_groups)
             else:
                 for layer in module:
                     if not isinstance(layer, ResBlock):

@@ -38,7 +38,8 @@ PROTOTYPES = {
     "fcwdm_linear": (_c_int, [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_p]),
     "fcwdm_conv3d_packed_elems": (_c_i64, [_c_i64, _c_i64, _c_int]),
     "fcwdm_conv3d_pack_weights": (_c_int, [_c_p, _c_p, _c_i64, _c_i64, _c_int, _c_p]),
-    "fcwdm_conv3d_fwd": (_c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64] + [_c_i64] * 6
+    "fcwdm_conv3d_fwd": (_c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64]
+                         + [_c_i64] * 6
                          + [_c_int, _c_p]),
 }
 

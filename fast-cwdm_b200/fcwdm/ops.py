@@ -176,9 +176,11 @@ def cl_to_planar(src, dst, C):
         native.call("fcwdm_cl_to_planar", _ptr(src), src.stride(0), _ptr(dst), N, C, S, st)
 
 
-def groupnorm_silu(x, y, stats, gamma, beta, N, S, C, G, eps=1e-5, silu=True):
+def groupnorm_silu(x, y, stats, gamma, beta, N, S, C, G, eps=1e-5, silu=True, have_stats=False):
+    """have_stats=True: `stats` was already filled by the producing conv's epilogue (fused statistics)."""
     with _on(x.device) as st:
-        native.call("fcwdm_groupnorm_stats", _ptr(x), x.stride(0), _ptr(stats), N, S, C, G, st)
+        if not have_stats:
+            native.call("fcwdm_groupnorm_stats", _ptr(x), x.stride(0), _ptr(stats), N, S, C, G, st)
         native.call("fcwdm_groupnorm_apply", _ptr(x), x.stride(0), _ptr(y), y.stride(0), _ptr(stats), _ptr(gamma),
                     _ptr(beta), N, S, C, G, float(eps), 1 if silu else 0, st)
 
@@ -210,13 +212,15 @@ def conv3d_pack_weights(w):
     return wp
 
 
-def conv3d_cl(x, wp, bias, y, dims, cin, cout, k, chan_bias=None, residual=None):
-    """x, y, residual: cl bf16 buffers (voxels, ld).  dims = (N, D, H, W)."""
+def conv3d_cl(x, wp, bias, y, dims, cin, cout, k, chan_bias=None, residual=None, gn_stats=None, gn_groups=0):
+    """x, y, residual: cl bf16 buffers (voxels, ld).  dims = (N, D, H, W).  gn_stats: optional PRE-ZEROED
+    (N, GN_STAT_REPLICAS, gn_groups, 2) float64 buffer that receives the GroupNorm statistics of y."""
     N, D, H, W = dims
     with _on(x.device) as st:
         native.call("fcwdm_conv3d_fwd", _ptr(x), x.stride(0), _ptr(wp), _ptr(bias), _ptr(chan_bias),
                     chan_bias.stride(0) if chan_bias is not None else 0, _ptr(residual),
-                    residual.stride(0) if residual is not None else 0, _ptr(y), y.stride(0), N, D, H, W, cin, cout, k, st)
+                    residual.stride(0) if residual is not None else 0, _ptr(y), y.stride(0), _ptr(gn_stats), gn_groups,
+                    N, D, H, W, cin, cout, k, st)
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -161,12 +161,17 @@ int fcwdm_linear(const float* x, const float* W, const float* b, float* y, int64
  *   finite, they meet zero weights), y cl bf16 (N,D,H,W,Cout) with voxel stride y_ld;
  *   y = conv(x, w) + bias[c] (+ chan_bias[n*cb_ld + c]: the timestep-embedding add, wunet.py:262)
  *       (+ residual[voxel*res_ld + c]: the ResBlock skip add, wunet.py:266, or `input_pyramid + h`, :759).
+ *   gn_stats (optional): the epilogue also accumulates the GroupNorm statistics of y (sum, sum of squares of the
+ *   stored bf16 values per (n, group), gn_groups groups of Cout/gn_groups channels) into a PRE-ZEROED
+ *   double [N][FCWDM_GN_STAT_REPLICAS][gn_groups][2] that fcwdm_groupnorm_apply consumes directly, so the
+ *   next GroupNorm needs no statistics pass over y.
  * ---------------------------------------------------------------------------------------------------- */
 int64_t fcwdm_conv3d_packed_elems(int64_t Cout, int64_t Cin, int ksize);
 int fcwdm_conv3d_pack_weights(const float* w, void* wp, int64_t Cout, int64_t Cin, int ksize, void* stream);
 int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, const float* bias, const float* chan_bias,
-                     int64_t cb_ld, const void* residual, int64_t res_ld, void* y, int64_t y_ld, int64_t N, int64_t D,
-                     int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize, void* stream);
+                     int64_t cb_ld, const void* residual, int64_t res_ld, void* y, int64_t y_ld, double* gn_stats,
+                     int64_t gn_groups, int64_t N, int64_t D, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                     int ksize, void* stream);
 
 #ifdef __cplusplus
 }

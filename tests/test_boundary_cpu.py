@@ -38,8 +38,8 @@ def test_argument_validation_without_gpu():
     assert lib.fcwdm_dwt3d_fwd(z, z, 0, 1, 1, 4, 4, 4, 0, 0, 0, 0, 0, 1.0, z) == -1        # null pointer
     assert lib.fcwdm_dwt3d_fwd(one, one, 7, 1, 1, 4, 4, 4, 0, 0, 0, 0, 0, 1.0, z) == -1      # bad dtype
     assert lib.fcwdm_dwt3d_fwd(z, z, 0, 0, 1, 4, 4, 4, 0, 0, 0, 0, 0, 1.0, z) == 0         # empty batch is a no-op
-    assert lib.fcwdm_conv3d_fwd(one, 64, one, z, z, 0, z, 0, one, 64, 1, 4, 4, 4, 64, 64, 5, z) == -2   # ksize 5
-    assert lib.fcwdm_conv3d_fwd(one, 32, one, z, z, 0, z, 0, one, 64, 1, 4, 4, 4, 64, 64, 3, z) == -1   # x_ld < Cin_p
+    assert lib.fcwdm_conv3d_fwd(one, 64, one, z, z, 0, z, 0, one, 64, z, 0, 1, 4, 4, 4, 64, 64, 5, z) == -2   # ksize 5
+    assert lib.fcwdm_conv3d_fwd(one, 32, one, z, z, 0, z, 0, one, 64, z, 0, 1, 4, 4, 4, 64, 64, 3, z) == -1   # x_ld < Cin_p
     assert lib.fcwdm_groupnorm_stats(one, 64, one, 1, 10, 64, 7, z) == -1                  # C % G != 0
 
 

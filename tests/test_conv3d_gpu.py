@@ -88,3 +88,24 @@ def test_conv3d_full_resolution_shape():
     """The dominant conv of CFG-W4 (64 -> 64 at 112x112x80), checked on sampled voxels incl. all borders."""
     got, ref = run_conv(1, 112, 112, 80, 64, 64, 3, seed=9)
     check(got, ref)
+
+
+@pytest.mark.parametrize("case", [(2, 5, 18, 10, 64, 64, 3, 32), (1, 4, 16, 16, 128, 128, 3, 32),
+                                  (1, 6, 10, 12, 64, 256, 1, 32), (2, 3, 7, 5, 32, 32, 3, 32)])
+def test_conv3d_fused_groupnorm_statistics(case):
+    """The epilogue's fused (sum, sumsq) per (n, group) of the stored bf16 output == statistics of that tensor."""
+    from fcwdm import ops
+    from gpu_util import bf16_round, from_cl, to_cl
+    N, D, H, W, cin, cout, k, G = case
+    g = torch.Generator().manual_seed(7)
+    x = bf16_round(torch.randn(N, cin, D, H, W, generator=g)).cuda()
+    w = (torch.randn(cout, cin, k, k, k, generator=g) / np.sqrt(cin * k ** 3)).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    xc, wp = to_cl(x), ops.conv3d_pack_weights(w)
+    yc = torch.zeros((N * D * H * W, (cout + 63) // 64 * 64), dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros((N, ops.GN_STAT_REPLICAS, G, 2), dtype=torch.float64, device="cuda")
+    ops.conv3d_cl(xc, wp, bias, yc, (N, D, H, W), cin, cout, k, gn_stats=stats, gn_groups=G)
+    y = from_cl(yc, (N, cout, D, H, W)).double().reshape(N, G, -1)
+    got = stats.sum(dim=1)
+    np.testing.assert_allclose(got[..., 0].cpu().numpy(), y.sum(-1).cpu().numpy(), rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(got[..., 1].cpu().numpy(), (y * y).sum(-1).cpu().numpy(), rtol=1e-4, atol=1e-2)
