@@ -16,7 +16,8 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-int conv3d_init_device();  // conv3d.cu
+int conv3d_init_device();       // conv3d.cu
+int conv3d_pair_init_device();  // conv3d_pair.cu
 
 bool pdl_enabled() {
     static int v = -1;
@@ -43,5 +44,7 @@ extern "C" int fcwdm_init(int device) {
     FCWDM_REQUIRE(major == 10, FCWDM_ERR_ARCH,
                   "fcwdm_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, major,
                   minor);
-    return fcwdm::conv3d_init_device();
+    int rc = fcwdm::conv3d_init_device();
+    if (rc) return rc;
+    return fcwdm::conv3d_pair_init_device();
 }

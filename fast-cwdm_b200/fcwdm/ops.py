@@ -223,6 +223,31 @@ def conv3d_cl(x, wp, bias, y, dims, cin, cout, k, chan_bias=None, residual=None,
                     N, D, H, W, cin, cout, k, st)
 
 
+def conv3d_pair_supported(cin, cout, k):
+    return bool(native.load().fcwdm_conv3d_pair_supported(cin, cout, k))
+
+
+def conv3d_pair_pack_weights(w):
+    """w: (Cout<=64, Cin<=64, 3, 3, 3) float32 CUDA -> packed bf16 [kh*3+kw][kd][Cout_p][64] for the CTA-pair kernel."""
+    _need_cuda(w, "conv3d_pair_pack_weights")
+    cout, cin = w.shape[0], w.shape[1]
+    wp = torch.empty(native.load().fcwdm_conv3d_pair_packed_elems(cout, cin), dtype=torch.bfloat16, device=w.device)
+    w = w.detach().float().contiguous()
+    with _on(w.device) as st:
+        native.call("fcwdm_conv3d_pair_pack_weights", _ptr(w), _ptr(wp), cout, cin, st)
+    return wp
+
+
+def conv3d_pair_cl(x, wp, bias, y, dims, cin, cout, chan_bias=None, residual=None, gn_stats=None, gn_groups=0):
+    """kd-fused two-CTA conv (3x3x3, C_in <= 64, C_out <= 64); same arguments as conv3d_cl."""
+    N, D, H, W = dims
+    with _on(x.device) as st:
+        native.call("fcwdm_conv3d_pair_fwd", _ptr(x), x.stride(0), _ptr(wp), _ptr(bias), _ptr(chan_bias),
+                    chan_bias.stride(0) if chan_bias is not None else 0, _ptr(residual),
+                    residual.stride(0) if residual is not None else 0, _ptr(y), y.stride(0), _ptr(gn_stats), gn_groups,
+                    N, D, H, W, cin, cout, st)
+
+
 # ----------------------------------------------------------------------------------------------------
 # diffusion step
 # ----------------------------------------------------------------------------------------------------

@@ -173,6 +173,20 @@ int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, const float* b
                      int64_t gn_groups, int64_t N, int64_t D, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
                      int ksize, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * K5b: the same 3x3x3 convolution for C_in <= 64 and C_out <= 64 (the full-resolution layers) as a kd-fused,
+ * two-CTA (cta_group::2) implicit GEMM with the weights resident in the CTA pair's shared memory
+ * (csrc/conv3d_pair.cu).  Same semantics and epilogue options as fcwdm_conv3d_fwd; its own weight packing
+ * [kh*3+kw][kd][C_out_p][64] (C_out_p = 16 or 64).  x must expose 64 readable channels per voxel (x_ld >= 64).
+ * ---------------------------------------------------------------------------------------------------- */
+int fcwdm_conv3d_pair_supported(int64_t Cin, int64_t Cout, int ksize);
+int64_t fcwdm_conv3d_pair_packed_elems(int64_t Cout, int64_t Cin);
+int fcwdm_conv3d_pair_pack_weights(const float* w, void* wp, int64_t Cout, int64_t Cin, void* stream);
+int fcwdm_conv3d_pair_fwd(const void* x, int64_t x_ld, const void* wp, const float* bias, const float* chan_bias,
+                          int64_t cb_ld, const void* residual, int64_t res_ld, void* y, int64_t y_ld,
+                          double* gn_stats, int64_t gn_groups, int64_t N, int64_t D, int64_t H, int64_t W,
+                          int64_t Cin, int64_t Cout, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,3 +109,59 @@ def test_conv3d_fused_groupnorm_statistics(case):
     got = stats.sum(dim=1)
     np.testing.assert_allclose(got[..., 0].cpu().numpy(), y.sum(-1).cpu().numpy(), rtol=1e-4, atol=1e-2)
     np.testing.assert_allclose(got[..., 1].cpu().numpy(), (y * y).sum(-1).cpu().numpy(), rtol=1e-4, atol=1e-2)
+
+
+def run_pair(N, D, H, W, cin, cout, use_bias=True, use_cb=False, use_res=False, seed=0, stats_groups=0):
+    from fcwdm import ops
+    from gpu_util import bf16_round, from_cl, to_cl
+    g = torch.Generator().manual_seed(seed)
+    x = bf16_round(torch.randn(N, cin, D, H, W, generator=g)).cuda()
+    w = bf16_round(torch.randn(cout, cin, 3, 3, 3, generator=g) / np.sqrt(cin * 27)).cuda()
+    bias = torch.randn(cout, generator=g).cuda() if use_bias else None
+    cb = torch.randn(N, cout, generator=g).cuda() if use_cb else None
+    res = bf16_round(torch.randn(N, cout, D, H, W, generator=g)).cuda() if use_res else None
+    xc = to_cl(x)
+    wp = ops.conv3d_pair_pack_weights(w)
+    yc = torch.zeros((N * D * H * W, (cout + 63) // 64 * 64), dtype=torch.bfloat16, device="cuda")
+    rc = to_cl(res) if use_res else None
+    stats = torch.zeros((N, ops.GN_STAT_REPLICAS, stats_groups, 2), dtype=torch.float64, device="cuda") if stats_groups else None
+    ops.conv3d_pair_cl(xc, wp, bias, yc, (N, D, H, W), cin, cout, chan_bias=cb, residual=rc, gn_stats=stats,
+                       gn_groups=stats_groups)
+    torch.cuda.synchronize()
+    got = from_cl(yc, (N, cout, D, H, W))
+    ref = F.conv3d(x, w, bias, padding=1)
+    if use_cb:
+        ref = ref + cb[:, :, None, None, None]
+    if use_res:
+        ref = ref + res
+    return got, ref, stats
+
+
+PAIR_CASES = [
+    (1, 4, 16, 16, 64, 64),        # one pair along W, one segment
+    (1, 9, 32, 8, 64, 64),         # pair along H
+    (2, 7, 18, 10, 64, 64),        # partial tiles, batch 2
+    (1, 23, 40, 24, 32, 64),       # several depth segments, C_in padded to 64 (stem conv)
+    (1, 12, 16, 16, 64, 8),        # output conv 64 -> 8 (N_TILE = 16)
+    (1, 5, 7, 5, 64, 32),          # tiny spatial dims, C_out 32
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv3d_pair_vs_torch(case):
+    got, ref, _ = run_pair(*case)
+    check(got, ref)
+
+
+def test_conv3d_pair_epilogue_and_stats():
+    got, ref, stats = run_pair(2, 6, 20, 16, 64, 64, use_cb=True, use_res=True, seed=5, stats_groups=32)
+    check(got, ref)
+    y = got.double().reshape(2, 32, -1)
+    s = stats.sum(dim=1)
+    np.testing.assert_allclose(s[..., 0].cpu().numpy(), y.sum(-1).cpu().numpy(), rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(s[..., 1].cpu().numpy(), (y * y).sum(-1).cpu().numpy(), rtol=1e-4, atol=1e-2)
+
+
+def test_conv3d_pair_full_resolution():
+    got, ref, _ = run_pair(1, 112, 112, 80, 64, 64, seed=9)
+    check(got, ref)
