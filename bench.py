@@ -200,18 +200,18 @@ def time_dominant_kernel(device, iters=20):
     S = LATENT[0] * LATENT[1] * LATENT[2]
     x = torch.randn((S, 64), device=device).to(torch.bfloat16)
     w = torch.randn((64, 64, 3, 3, 3), device=device) * 0.02
-    wp = ops.conv3d_pack_weights(w)
+    wp = ops.conv3d_pair_pack_weights(w)
     b = torch.zeros(64, device=device)
     y = torch.empty((S, 64), dtype=torch.bfloat16, device=device)
     flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=device)
     for _ in range(3):
-        ops.conv3d_cl(x, wp, b, y, (1,) + LATENT, 64, 64, 3)
+        ops.conv3d_pair_cl(x, wp, b, y, (1,) + LATENT, 64, 64)
     total = 0.0
     for _ in range(iters):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.conv3d_cl(x, wp, b, y, (1,) + LATENT, 64, 64, 3)
+        ops.conv3d_pair_cl(x, wp, b, y, (1,) + LATENT, 64, 64)
         e1.record()
         e1.synchronize()
         total += e0.elapsed_time(e1)
@@ -346,7 +346,7 @@ def run_gpu(args):
         ach = flop / (ms_k * 1e-3) / 1e12
         result["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                               "frac": ach / peaks["tf_burst"], "traffic": None,
-                              "kernel": "conv3d_igemm_kernel<64,4,3> 64->64 @112x112x80",
+                              "kernel": "conv3d_pair_kernel<64> (cta_group::2, kd-fused) 64->64 @112x112x80",
                               "us_per_launch": ms_k * 1e3, "flop_per_launch": flop}
         hb = time_haar(device)
         result["secondary"] = {"dwt3d_gbs": hb["dwt3d"], "idwt3d_gbs": hb["idwt3d"], "hbm_peak_gbs": peaks["hbm"],

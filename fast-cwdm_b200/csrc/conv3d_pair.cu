@@ -155,6 +155,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     const uint32_t tmem_slot = b_full + 8;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* wstat = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));
+    float* sbias = reinterpret_cast<float*>(smem_raw + (bars + 512 - smem_u32(smem_raw)));   // [N_TILE]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -286,16 +287,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         uint32_t G = 0;
         for (int item = cluster_id; item < args.num_items; item += num_clusters) {
             const PairItem it = decode_item(item, args, (int)rank);
-            if (want_stats && it.n != cur_n) {
-                if (cur_n >= 0) p_flush_gn_stats(wstat, args, cur_n, ew, lane);
+            if (it.n != cur_n) {
+                if (want_stats && cur_n >= 0) p_flush_gn_stats(wstat, args, cur_n, ew, lane);
                 cur_n = it.n;
+                // per-sample additive term bias[c] + chan_bias[n][c], staged once in shared memory (broadcast reads)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (row < N_TILE) {
+                    float bv = 0.f;
+                    if (row < args.Cout) {
+                        if (args.bias != nullptr) bv += __ldg(args.bias + row);
+                        if (args.chan_bias != nullptr) bv += __ldg(args.chan_bias + (long long)it.n * args.cb_ld + row);
+                    }
+                    sbias[row] = bv;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             const int h = it.h0 + hh, w = it.w0 + ww;
             const bool hw_ok = (h < args.H) && (w < args.W);
             for (int i = 0; i < it.L + 4; ++i, ++G) {
                 const uint32_t ring = G % Cfg::RING;
-                mbar_wait(acc_full + 8 * ring, (G / Cfg::RING) & 1);
-                tc_fence_after();
                 const uint32_t v = 5 - (G % 6);
                 const uint32_t main_col = v * N_TILE;
                 const bool split = v < 2;                                 // slots 6 / 7 hold the other half
@@ -304,80 +314,84 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
                 const bool real = (i >= 2) && (i < it.L + 2);             // dummy planes are drained and dropped
                 const bool ok = real && hw_ok;
                 const long long vox = (((long long)it.n * args.D + d) * args.H + h) * args.W + w;
-#pragma unroll 1
-                for (int c0 = 0; c0 < N_TILE; c0 += 16) {
-                    uint32_t acc[16];
-                    tmem_ld_x16(lane_base + main_col + c0, acc);
-                    if (split) {
-                        uint32_t acc2[16];
-                        tmem_ld_x16(lane_base + extra_col + c0, acc2);
-                        tmem_ld_wait();
+                // residual row: issue the global loads before waiting for the accumulator
+                uint4 res[N_TILE / 8];
+                if (ok && args.residual != nullptr) {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) acc[e] = __float_as_uint(__uint_as_float(acc[e]) + __uint_as_float(acc2[e]));
-                        tmem_st_zero_x16(lane_base + extra_col + c0);
-                    } else {
-                        tmem_ld_wait();
-                    }
-                    tmem_st_zero_x16(lane_base + main_col + c0);
-                    if (real) {                                           // warp-uniform
+                    for (int g = 0; g < N_TILE / 8; ++g)
+                        if (g * 8 < args.Cout)
+                            res[g] = *reinterpret_cast<const uint4*>(args.residual + vox * args.res_ld + g * 8);
+                }
+                mbar_wait(acc_full + 8 * ring, (G / Cfg::RING) & 1);
+                tc_fence_after();
+                // drain the whole accumulator row (N_TILE fp32 columns) with all TMEM loads in flight at once
+                uint32_t acc[N_TILE];
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            const int co = c0 + g * 8;
-                            if (co < args.Cout) {
-                                float vv[8];
+                for (int c0 = 0; c0 < N_TILE; c0 += 16) tmem_ld_x16(lane_base + main_col + c0, acc + c0);
+                if (split) {
+                    uint32_t acc2[N_TILE];
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) vv[e] = __uint_as_float(acc[g * 8 + e]);
-                                if (args.bias != nullptr) {
-                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + co));
-                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + co + 4));
-                                    vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-                                    vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+                    for (int c0 = 0; c0 < N_TILE; c0 += 16) tmem_ld_x16(lane_base + extra_col + c0, acc2 + c0);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < N_TILE; ++e)
+                        acc[e] = __float_as_uint(__uint_as_float(acc[e]) + __uint_as_float(acc2[e]));
+#pragma unroll
+                    for (int c0 = 0; c0 < N_TILE; c0 += 16) tmem_st_zero_x16(lane_base + extra_col + c0);
+                } else {
+                    tmem_ld_wait();
+                }
+#pragma unroll
+                for (int c0 = 0; c0 < N_TILE; c0 += 16) tmem_st_zero_x16(lane_base + main_col + c0);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8 * ring);    // slots free for the MMA again
+                if (real) {                                               // warp-uniform
+#pragma unroll
+                    for (int g = 0; g < N_TILE / 8; ++g) {
+                        const int co = g * 8;
+                        if (co < args.Cout) {
+                            float vv[8];
+                            const float4 b0 = *reinterpret_cast<const float4*>(sbias + co);
+                            const float4 b1 = *reinterpret_cast<const float4*>(sbias + co + 4);
+                            vv[0] = __uint_as_float(acc[co + 0]) + b0.x; vv[1] = __uint_as_float(acc[co + 1]) + b0.y;
+                            vv[2] = __uint_as_float(acc[co + 2]) + b0.z; vv[3] = __uint_as_float(acc[co + 3]) + b0.w;
+                            vv[4] = __uint_as_float(acc[co + 4]) + b1.x; vv[5] = __uint_as_float(acc[co + 5]) + b1.y;
+                            vv[6] = __uint_as_float(acc[co + 6]) + b1.z; vv[7] = __uint_as_float(acc[co + 7]) + b1.w;
+                            if (ok && args.residual != nullptr) {
+                                float rr[8];
+                                unpack8(res[g], rr);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) vv[e] += rr[e];
+                            }
+                            const uint4 packed = pack8(vv);
+                            if (ok) *reinterpret_cast<uint4*>(args.y + vox * args.y_ld + co) = packed;
+                            if (want_stats) {
+                                float vr[8];
+                                unpack8(packed, vr);
+                                if (!ok) {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) vr[e] = 0.f;
                                 }
-                                if (args.chan_bias != nullptr) {
-                                    const float* cbp = args.chan_bias + (long long)it.n * args.cb_ld + co;
-                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(cbp));
-                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(cbp + 4));
-                                    vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-                                    vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
-                                }
-                                if (ok && args.residual != nullptr) {
-                                    float rr[8];
-                                    unpack8(*reinterpret_cast<const uint4*>(args.residual + vox * args.res_ld + co), rr);
+                                switch (args.gn_cpg) {
+                                    case 1: p_gn_accumulate<1>(vr, my_stat, co, lane); break;
+                                    case 2: p_gn_accumulate<2>(vr, my_stat, co, lane); break;
+                                    case 4: p_gn_accumulate<4>(vr, my_stat, co, lane); break;
+                                    default: {
+                                        float a2[2] = {0.f, 0.f};
 #pragma unroll
-                                    for (int e = 0; e < 8; ++e) vv[e] += rr[e];
-                                }
-                                const uint4 packed = pack8(vv);
-                                if (ok) *reinterpret_cast<uint4*>(args.y + vox * args.y_ld + co) = packed;
-                                if (want_stats) {
-                                    float vr[8];
-                                    unpack8(packed, vr);
-                                    if (!ok) {
-#pragma unroll
-                                        for (int e = 0; e < 8; ++e) vr[e] = 0.f;
-                                    }
-                                    switch (args.gn_cpg) {
-                                        case 1: p_gn_accumulate<1>(vr, my_stat, co, lane); break;
-                                        case 2: p_gn_accumulate<2>(vr, my_stat, co, lane); break;
-                                        case 4: p_gn_accumulate<4>(vr, my_stat, co, lane); break;
-                                        default: {
-                                            float a2[2] = {0.f, 0.f};
-#pragma unroll
-                                            for (int e = 0; e < 8; ++e) {
-                                                a2[0] += vr[e];
-                                                a2[1] = fmaf(vr[e], vr[e], a2[1]);
-                                            }
-                                            p_reduce_scatter<2>(a2, lane, my_stat + 2 * (co / args.gn_cpg));
-                                        } break;
-                                    }
+                                        for (int e = 0; e < 8; ++e) {
+                                            a2[0] += vr[e];
+                                            a2[1] = fmaf(vr[e], vr[e], a2[1]);
+                                        }
+                                        p_reduce_scatter<2>(a2, lane, my_stat + 2 * (co / args.gn_cpg));
+                                    } break;
                                 }
                             }
                         }
                     }
                 }
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8 * ring);
             }
         }
         if (want_stats && cur_n >= 0) p_flush_gn_stats(wstat, args, cur_n, ew, lane);

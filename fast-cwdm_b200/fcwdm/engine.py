@@ -24,7 +24,7 @@ def _ld(c):
 
 
 class _Packed:
-    __slots__ = ("wp", "bias", "cin", "cout", "k")
+    __slots__ = ("wp", "bias", "cin", "cout", "k", "pair")
 
 
 class WavUNetEngine:
@@ -38,7 +38,10 @@ class WavUNetEngine:
         self._arena = None
         self._arena_pos = 0
         import os
-        self.fuse_stats = os.environ.get("FCWDM_NO_FUSED_STATS", "0") != "1"
+        # fused GroupNorm statistics in the conv epilogue: measured break-even against the separate (HBM-roofline)
+        # statistics pass in round 1, so opt-in
+        self.fuse_stats = os.environ.get("FCWDM_FUSED_STATS", "0") == "1"
+        self.use_pair = os.environ.get("FCWDM_NO_PAIR", "0") != "1"
 
     # ------------------------------------------------------------------ weights
     def _signature(self):
@@ -60,7 +63,9 @@ class WavUNetEngine:
                     raise FcwdmError("WavUNetModel parameters are on the CPU; call model.to(cuda_device) first "
                                      "(the fcwdm denoiser has no CPU path)")
                 pk = _Packed()
-                pk.wp = ops.conv3d_pack_weights(mod.weight)
+                # C_in, C_out <= 64 (the full-resolution layers): kd-fused CTA-pair kernel with resident weights
+                pk.pair = self.use_pair and ops.conv3d_pair_supported(mod.in_channels, mod.out_channels, k)
+                pk.wp = ops.conv3d_pair_pack_weights(mod.weight) if pk.pair else ops.conv3d_pack_weights(mod.weight)
                 pk.bias = mod.bias.detach().float().contiguous() if mod.bias is not None else None
                 pk.cout, pk.cin, pk.k = mod.out_channels, mod.in_channels, k
                 self._conv[id(mod)] = pk
@@ -111,8 +116,12 @@ class WavUNetEngine:
         if self.fuse_stats and stats_groups and stats_groups <= 32 and (cpg in (1, 2, 4) or (cpg and cpg % 8 == 0)):
             stats = self._stats_slot(N, stats_groups, x.device)
             self._stats[id(y)] = (stats, stats_groups, y)     # holding y keeps its id unique until consumed
-        ops.conv3d_cl(x, pk.wp, pk.bias, y, (N,) + tuple(dims), pk.cin, pk.cout, pk.k, chan_bias=chan_bias,
-                      residual=residual, gn_stats=stats, gn_groups=stats_groups if stats is not None else 0)
+        if pk.pair:
+            ops.conv3d_pair_cl(x, pk.wp, pk.bias, y, (N,) + tuple(dims), pk.cin, pk.cout, chan_bias=chan_bias,
+                               residual=residual, gn_stats=stats, gn_groups=stats_groups if stats is not None else 0)
+        else:
+            ops.conv3d_cl(x, pk.wp, pk.bias, y, (N,) + tuple(dims), pk.cin, pk.cout, pk.k, chan_bias=chan_bias,
+                          residual=residual, gn_stats=stats, gn_groups=stats_groups if stats is not None else 0)
         return y
 
     def _stats_slot(self, N, G, device):
