@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
     const uint32_t tmem_slot = tmem_empty + 8 * Cfg::ACC_STAGES;   // 4 B: TMEM base address
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* wstat = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));   // [4 warps][32 groups][2]
+    float* sbias = reinterpret_cast<float*>(smem_raw + (bars + 512 - smem_u32(smem_raw)));    // [N_TILE] bias + chan_bias of the current tile
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -325,13 +326,27 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
             my_stat[lane + 32] = 0.f;
             __syncwarp();
         }
-        int cur_n = -1;
+        int cur_n = -1, cur_n0 = -1;
         uint32_t acc_it = 0;
         for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++acc_it) {
             const TileCoord tc = decode_tile(tile, args, TD, N_TILE);
-            if (want_stats && tc.n != cur_n) {
-                if (cur_n >= 0) flush_gn_stats(wstat, args, cur_n, ew, lane);
+            if (tc.n != cur_n || tc.n0 != cur_n0) {
+                if (want_stats && tc.n != cur_n && cur_n >= 0) flush_gn_stats(wstat, args, cur_n, ew, lane);
                 cur_n = tc.n;
+                cur_n0 = tc.n0;
+                // additive per-channel term bias[c] + chan_bias[n][c] of this tile's N_TILE channels, staged once in
+                // shared memory (every thread then reads it with broadcast 128-bit loads)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (row < N_TILE) {
+                    const int co = tc.n0 + row;
+                    float bv = 0.f;
+                    if (co < args.Cout) {
+                        if (args.bias != nullptr) bv += __ldg(args.bias + co);
+                        if (args.chan_bias != nullptr) bv += __ldg(args.chan_bias + (long long)tc.n * args.cb_ld + co);
+                    }
+                    sbias[row] = bv;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             const uint32_t as = acc_it % Cfg::ACC_STAGES, aph = (acc_it / Cfg::ACC_STAGES) & 1;
             mbar_wait(tmem_full + 8 * as, aph);
@@ -344,34 +359,37 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
                 const bool ok = hw_ok && (d < args.D);
                 const long long vox = (((long long)tc.n * args.D + d) * args.H + h) * args.W + w;
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * Cfg::ACC_COLS + j * N_TILE;
+                // 64 accumulator columns at a time: all TMEM loads and the residual row loads are in flight together
+                // (the epilogue has to keep up with one tile of MMAs; a serial 16-column loop did not)
+                constexpr int COLS = N_TILE < 64 ? N_TILE : 64;
 #pragma unroll 1
-                for (int c0 = 0; c0 < N_TILE; c0 += Cfg::CHUNK) {
-                    uint32_t acc[16];
-                    tmem_ld_x16(taddr + c0, acc);
+                for (int c0 = 0; c0 < N_TILE; c0 += COLS) {
+                    uint4 res[COLS / 8];
+                    if (ok && args.residual != nullptr) {
+#pragma unroll
+                        for (int g = 0; g < COLS / 8; ++g)
+                            if (tc.n0 + c0 + g * 8 < args.Cout)
+                                res[g] = *reinterpret_cast<const uint4*>(args.residual + vox * args.res_ld + tc.n0 + c0 + g * 8);
+                    }
+                    uint32_t acc[COLS];
+#pragma unroll
+                    for (int q = 0; q < COLS; q += 16) tmem_ld_x16(taddr + c0 + q, acc + q);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const int co = tc.n0 + c0 + g * 8;
+                    for (int g = 0; g < COLS / 8; ++g) {
+                        const int col = c0 + g * 8;
+                        const int co = tc.n0 + col;
                         if (co < args.Cout) {                                   // warp-uniform
                             float v[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[g * 8 + e]);
-                            if (args.bias != nullptr) {
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + co));
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + co + 4));
-                                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                            }
-                            if (args.chan_bias != nullptr) {
-                                const float* cbp = args.chan_bias + (long long)tc.n * args.cb_ld + co;
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(cbp));
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(cbp + 4));
-                                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                            }
+                            const float4 b0 = *reinterpret_cast<const float4*>(sbias + col);
+                            const float4 b1 = *reinterpret_cast<const float4*>(sbias + col + 4);
+                            v[0] = __uint_as_float(acc[g * 8 + 0]) + b0.x; v[1] = __uint_as_float(acc[g * 8 + 1]) + b0.y;
+                            v[2] = __uint_as_float(acc[g * 8 + 2]) + b0.z; v[3] = __uint_as_float(acc[g * 8 + 3]) + b0.w;
+                            v[4] = __uint_as_float(acc[g * 8 + 4]) + b1.x; v[5] = __uint_as_float(acc[g * 8 + 5]) + b1.y;
+                            v[6] = __uint_as_float(acc[g * 8 + 6]) + b1.z; v[7] = __uint_as_float(acc[g * 8 + 7]) + b1.w;
                             if (ok && args.residual != nullptr) {
                                 float rr[8];
-                                unpack8(*reinterpret_cast<const uint4*>(args.residual + vox * args.res_ld + co), rr);
+                                unpack8(res[g], rr);
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) v[e] += rr[e];
                             }
