@@ -94,6 +94,7 @@ __device__ __forceinline__ void p_halve_step(float* a, int lane) {
 }
 template <int V>
 __device__ __forceinline__ void p_reduce_scatter(float* a, int lane, float* dst) {
+    if constexpr (V == 32) { p_halve_step<32, 16>(a, lane); p_halve_step<16, 8>(a, lane); p_halve_step<8, 4>(a, lane); p_halve_step<4, 2>(a, lane); p_halve_step<2, 1>(a, lane); }
     if constexpr (V == 16) { p_halve_step<16, 16>(a, lane); p_halve_step<8, 8>(a, lane); p_halve_step<4, 4>(a, lane); p_halve_step<2, 2>(a, lane); }
     if constexpr (V == 8) { p_halve_step<8, 16>(a, lane); p_halve_step<4, 8>(a, lane); p_halve_step<2, 4>(a, lane); }
     if constexpr (V == 4) { p_halve_step<4, 16>(a, lane); p_halve_step<2, 8>(a, lane); }
@@ -102,36 +103,39 @@ __device__ __forceinline__ void p_reduce_scatter(float* a, int lane, float* dst)
     for (int off = 16 / V; off > 0; off >>= 1) a[0] += __shfl_xor_sync(0xffffffffu, a[0], off);
     if ((lane & (32 / V - 1)) == 0) dst[lane / (32 / V)] += a[0];
 }
-template <int CPG>
-__device__ __forceinline__ void p_gn_accumulate(const float* vr, float* my_stat, int co, int lane) {
-    constexpr int V = 2 * (8 / CPG);
-    float a[V];
+template <int V>
+__device__ __forceinline__ void p_zero_then_reduce(float* a, int lane, float* dst) {
+    dst[lane] = 0.f;
+    __syncwarp();
+    float tmp[V];
 #pragma unroll
-    for (int g = 0; g < 8 / CPG; ++g) {
-        float s = 0.f, q = 0.f;
-#pragma unroll
-        for (int e = 0; e < CPG; ++e) {
-            s += vr[g * CPG + e];
-            q = fmaf(vr[g * CPG + e], vr[g * CPG + e], q);
-        }
-        a[2 * g] = s;
-        a[2 * g + 1] = q;
-    }
-    p_reduce_scatter<V>(a, lane, my_stat + 2 * (co / CPG));
+    for (int i = 0; i < V; ++i) tmp[i] = a[i];
+    p_reduce_scatter<V>(tmp, lane, dst);
+    __syncwarp();
 }
-__device__ __forceinline__ void p_flush_gn_stats(float* wstat, const PairArgs& args, int n, int ew, int lane) {
+// Per-thread channel-pair sums (ps: sum, pq: sum of squares; N_TILE/2 each) -> warp totals (halving butterfly) ->
+// shared memory [warp][2][N_TILE/2] -> one fp64 atomic per (group, component), groups = runs of cpg/2 pairs.
+template <int N_TILE>
+__device__ __forceinline__ void p_flush_pair_stats(float* ps, float* pq, float* wstat, const PairArgs& args, int n,
+                                                   int ew, int lane) {
+    constexpr int P = N_TILE / 2;                 // 32 (N_TILE = 64) or 8 (N_TILE = 16)
+    float* mine = wstat + ew * 64;
+    p_zero_then_reduce<P>(ps, lane, mine);
+    p_zero_then_reduce<P>(pq, lane, mine + 32);
     asm volatile("bar.sync 1, 128;" ::: "memory");
     const int e = ew * 32 + lane;
     if (e < 2 * args.gn_groups) {
-        const double v = (double)wstat[e] + (double)wstat[64 + e] + (double)wstat[128 + e] + (double)wstat[192 + e];
+        const int g = e >> 1, comp = e & 1, ppg = args.gn_cpg >> 1;
+        double v = 0.0;
+        for (int wq = 0; wq < 4; ++wq)
+            for (int j = 0; j < ppg; ++j) v += (double)wstat[wq * 64 + comp * 32 + g * ppg + j];
         double* dst = args.gn_stats +
                       (((long long)n * FCWDM_GN_STAT_REPLICAS + (blockIdx.x % FCWDM_GN_STAT_REPLICAS)) * args.gn_groups) * 2;
         atomicAdd(dst + e, v);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    wstat[ew * 64 + lane] = 0.f;
-    wstat[ew * 64 + 32 + lane] = 0.f;
-    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < P; ++i) ps[i] = pq[i] = 0.f;
 }
 
 constexpr int kPWarpProdA = 4, kPWarpProdB = 5, kPWarpAlloc = 6, kPWarpMma = 7;
@@ -269,13 +273,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         const int hh = row >> 3, ww = row & 7;
         const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
         const uint32_t acc_empty_leader = mapa_u32(acc_empty, 0);
+        // Fused GroupNorm statistics of the output: per-thread fp32 sums over CHANNEL PAIRS (exact for any even number
+        // of channels per group) kept in registers across all planes of the sample, reduced across lanes only when
+        // the sample index changes / at exit -- the per-plane cost is 2 FADD/FFMA per channel.
         const bool want_stats = args.gn_stats != nullptr;
-        float* my_stat = wstat + ew * 64;
-        if (want_stats) {
-            my_stat[lane] = 0.f;
-            my_stat[lane + 32] = 0.f;
-            __syncwarp();
-        }
+        float ps[N_TILE / 2], pq[N_TILE / 2];
+#pragma unroll
+        for (int e = 0; e < N_TILE / 2; ++e) ps[e] = pq[e] = 0.f;
         // initial state: all accumulator slots zero, every ring entry "empty" (phase 0 of acc_empty)
         for (int c = 0; c < 8 * N_TILE; c += 16) tmem_st_zero_x16(lane_base + c);
         tmem_st_wait();
@@ -285,10 +289,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
             for (int r = 0; r < Cfg::RING; ++r) mbar_arrive_cluster(acc_empty_leader + 8 * r);
         int cur_n = -1;
         uint32_t G = 0;
+        constexpr int HALF = N_TILE < 32 ? N_TILE : 32;          // accumulator columns drained per batch of TMEM loads
         for (int item = cluster_id; item < args.num_items; item += num_clusters) {
             const PairItem it = decode_item(item, args, (int)rank);
             if (it.n != cur_n) {
-                if (want_stats && cur_n >= 0) p_flush_gn_stats(wstat, args, cur_n, ew, lane);
+                if (want_stats && cur_n >= 0) p_flush_pair_stats<N_TILE>(ps, pq, wstat, args, cur_n, ew, lane);
                 cur_n = it.n;
                 // per-sample additive term bias[c] + chan_bias[n][c], staged once in shared memory (broadcast reads)
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -313,88 +318,87 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
                 const int d = it.d_begin - 2 + i;
                 const bool real = (i >= 2) && (i < it.L + 2);             // dummy planes are drained and dropped
                 const bool ok = real && hw_ok;
+                const bool use_res = ok && args.residual != nullptr;
                 const long long vox = (((long long)it.n * args.D + d) * args.H + h) * args.W + w;
-                // residual row: issue the global loads before waiting for the accumulator
-                uint4 res[N_TILE / 8];
-                if (ok && args.residual != nullptr) {
+                // first half of the residual row: in flight while we wait for the accumulator
+                uint4 res[HALF / 8];
+                if (use_res) {
 #pragma unroll
-                    for (int g = 0; g < N_TILE / 8; ++g)
-                        if (g * 8 < args.Cout)
-                            res[g] = *reinterpret_cast<const uint4*>(args.residual + vox * args.res_ld + g * 8);
+                    for (int g = 0; g < HALF / 8; ++g)
+                        if (g * 8 < args.Cout) res[g] = *reinterpret_cast<const uint4*>(args.residual + vox * args.res_ld + g * 8);
                 }
                 mbar_wait(acc_full + 8 * ring, (G / Cfg::RING) & 1);
                 tc_fence_after();
-                // drain the whole accumulator row (N_TILE fp32 columns) with all TMEM loads in flight at once
-                uint32_t acc[N_TILE];
 #pragma unroll
-                for (int c0 = 0; c0 < N_TILE; c0 += 16) tmem_ld_x16(lane_base + main_col + c0, acc + c0);
-                if (split) {
-                    uint32_t acc2[N_TILE];
+                for (int c0 = 0; c0 < N_TILE; c0 += HALF) {
+                    // drain HALF fp32 columns (both physical halves of a split plane) with all TMEM loads in flight,
+                    // zero them for the next use of the slot
+                    uint32_t acc[HALF];
 #pragma unroll
-                    for (int c0 = 0; c0 < N_TILE; c0 += 16) tmem_ld_x16(lane_base + extra_col + c0, acc2 + c0);
-                    tmem_ld_wait();
+                    for (int q = 0; q < HALF; q += 16) tmem_ld_x16(lane_base + main_col + c0 + q, acc + q);
+                    if (split) {
+                        uint32_t acc2[HALF];
 #pragma unroll
-                    for (int e = 0; e < N_TILE; ++e)
-                        acc[e] = __float_as_uint(__uint_as_float(acc[e]) + __uint_as_float(acc2[e]));
+                        for (int q = 0; q < HALF; q += 16) tmem_ld_x16(lane_base + extra_col + c0 + q, acc2 + q);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int c0 = 0; c0 < N_TILE; c0 += 16) tmem_st_zero_x16(lane_base + extra_col + c0);
-                } else {
-                    tmem_ld_wait();
-                }
+                        for (int e = 0; e < HALF; ++e)
+                            acc[e] = __float_as_uint(__uint_as_float(acc[e]) + __uint_as_float(acc2[e]));
 #pragma unroll
-                for (int c0 = 0; c0 < N_TILE; c0 += 16) tmem_st_zero_x16(lane_base + main_col + c0);
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8 * ring);    // slots free for the MMA again
-                if (real) {                                               // warp-uniform
+                        for (int q = 0; q < HALF; q += 16) tmem_st_zero_x16(lane_base + extra_col + c0 + q);
+                    } else {
+                        tmem_ld_wait();
+                    }
 #pragma unroll
-                    for (int g = 0; g < N_TILE / 8; ++g) {
-                        const int co = g * 8;
-                        if (co < args.Cout) {
-                            float vv[8];
-                            const float4 b0 = *reinterpret_cast<const float4*>(sbias + co);
-                            const float4 b1 = *reinterpret_cast<const float4*>(sbias + co + 4);
-                            vv[0] = __uint_as_float(acc[co + 0]) + b0.x; vv[1] = __uint_as_float(acc[co + 1]) + b0.y;
-                            vv[2] = __uint_as_float(acc[co + 2]) + b0.z; vv[3] = __uint_as_float(acc[co + 3]) + b0.w;
-                            vv[4] = __uint_as_float(acc[co + 4]) + b1.x; vv[5] = __uint_as_float(acc[co + 5]) + b1.y;
-                            vv[6] = __uint_as_float(acc[co + 6]) + b1.z; vv[7] = __uint_as_float(acc[co + 7]) + b1.w;
-                            if (ok && args.residual != nullptr) {
-                                float rr[8];
-                                unpack8(res[g], rr);
+                    for (int q = 0; q < HALF; q += 16) tmem_st_zero_x16(lane_base + main_col + c0 + q);
+                    if (c0 + HALF >= N_TILE) {                            // whole row drained: slots free for the MMA again
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8 * ring);
+                    }
+                    if (real) {                                           // warp-uniform
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) vv[e] += rr[e];
-                            }
-                            const uint4 packed = pack8(vv);
-                            if (ok) *reinterpret_cast<uint4*>(args.y + vox * args.y_ld + co) = packed;
-                            if (want_stats) {
-                                float vr[8];
-                                unpack8(packed, vr);
-                                if (!ok) {
+                        for (int g = 0; g < HALF / 8; ++g) {
+                            const int co = c0 + g * 8;
+                            if (co < args.Cout) {
+                                float vv[8];
+                                const float4 b0 = *reinterpret_cast<const float4*>(sbias + co);
+                                const float4 b1 = *reinterpret_cast<const float4*>(sbias + co + 4);
+                                vv[0] = __uint_as_float(acc[g * 8 + 0]) + b0.x; vv[1] = __uint_as_float(acc[g * 8 + 1]) + b0.y;
+                                vv[2] = __uint_as_float(acc[g * 8 + 2]) + b0.z; vv[3] = __uint_as_float(acc[g * 8 + 3]) + b0.w;
+                                vv[4] = __uint_as_float(acc[g * 8 + 4]) + b1.x; vv[5] = __uint_as_float(acc[g * 8 + 5]) + b1.y;
+                                vv[6] = __uint_as_float(acc[g * 8 + 6]) + b1.z; vv[7] = __uint_as_float(acc[g * 8 + 7]) + b1.w;
+                                if (use_res) {
+                                    float rr[8];
+                                    unpack8(res[g], rr);
 #pragma unroll
-                                    for (int e = 0; e < 8; ++e) vr[e] = 0.f;
+                                    for (int e = 0; e < 8; ++e) vv[e] += rr[e];
                                 }
-                                switch (args.gn_cpg) {
-                                    case 1: p_gn_accumulate<1>(vr, my_stat, co, lane); break;
-                                    case 2: p_gn_accumulate<2>(vr, my_stat, co, lane); break;
-                                    case 4: p_gn_accumulate<4>(vr, my_stat, co, lane); break;
-                                    default: {
-                                        float a2[2] = {0.f, 0.f};
+                                const uint4 packed = pack8(vv);
+                                if (ok) *reinterpret_cast<uint4*>(args.y + vox * args.y_ld + co) = packed;
+                                if (want_stats && ok) {                   // statistics of the STORED (bf16) values
+                                    float vr[8];
+                                    unpack8(packed, vr);
 #pragma unroll
-                                        for (int e = 0; e < 8; ++e) {
-                                            a2[0] += vr[e];
-                                            a2[1] = fmaf(vr[e], vr[e], a2[1]);
-                                        }
-                                        p_reduce_scatter<2>(a2, lane, my_stat + 2 * (co / args.gn_cpg));
-                                    } break;
+                                    for (int e = 0; e < 4; ++e) {
+                                        ps[(co >> 1) + e] += vr[2 * e] + vr[2 * e + 1];
+                                        pq[(co >> 1) + e] = fmaf(vr[2 * e], vr[2 * e], fmaf(vr[2 * e + 1], vr[2 * e + 1], pq[(co >> 1) + e]));
+                                    }
                                 }
                             }
+                        }
+                        if (use_res && c0 + HALF < N_TILE) {              // next half of the residual row
+#pragma unroll
+                            for (int g = 0; g < HALF / 8; ++g)
+                                if (c0 + HALF + g * 8 < args.Cout)
+                                    res[g] = *reinterpret_cast<const uint4*>(args.residual + vox * args.res_ld + c0 + HALF + g * 8);
                         }
                     }
                 }
             }
         }
-        if (want_stats && cur_n >= 0) p_flush_gn_stats(wstat, args, cur_n, ew, lane);
+        if (want_stats && cur_n >= 0) p_flush_pair_stats<N_TILE>(ps, pq, wstat, args, cur_n, ew, lane);
     }
 
     tc_fence_before();
@@ -512,8 +516,8 @@ extern "C" int fcwdm_conv3d_pair_fwd(const void* x, int64_t x_ld, const void* wp
         FCWDM_REQUIRE(gn_groups > 0 && gn_groups <= 32 && Cout % gn_groups == 0, FCWDM_ERR_UNSUPPORTED,
                       "fcwdm_conv3d_pair_fwd: fused GroupNorm statistics need 1 <= groups <= 32 dividing C_out");
         const int64_t cpg = Cout / gn_groups;
-        FCWDM_REQUIRE(cpg == 1 || cpg == 2 || cpg == 4 || cpg % 8 == 0, FCWDM_ERR_UNSUPPORTED,
-                      "fcwdm_conv3d_pair_fwd: channels/group must be in {1,2,4,8k}");
+        FCWDM_REQUIRE(cpg % 2 == 0, FCWDM_ERR_UNSUPPORTED,
+                      "fcwdm_conv3d_pair_fwd: fused statistics need an even number of channels per group");
     }
     if (N * D * H * W == 0) return FCWDM_OK;
     if (g_encode_p == nullptr) {

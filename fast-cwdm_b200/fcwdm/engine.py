@@ -40,7 +40,8 @@ class WavUNetEngine:
         import os
         # fused GroupNorm statistics in the conv epilogue: measured break-even against the separate (HBM-roofline)
         # statistics pass in round 1, so opt-in
-        self.fuse_stats = os.environ.get("FCWDM_FUSED_STATS", "0") == "1"
+        self.fuse_stats = os.environ.get("FCWDM_FUSED_STATS", "0") == "1"          # single-CTA kernel: opt-in
+        self.fuse_stats_pair = os.environ.get("FCWDM_NO_FUSED_STATS_PAIR", "0") != "1"  # pair kernel: register sums, free
         self.use_pair = os.environ.get("FCWDM_NO_PAIR", "0") != "1"
 
     # ------------------------------------------------------------------ weights
@@ -113,7 +114,9 @@ class WavUNetEngine:
         y = self._buf(rows, pk.cout, x.device, out_ld)
         stats = None
         cpg = pk.cout // stats_groups if stats_groups and pk.cout % stats_groups == 0 else 0
-        if self.fuse_stats and stats_groups and stats_groups <= 32 and (cpg in (1, 2, 4) or (cpg and cpg % 8 == 0)):
+        ok_pair = pk.pair and self.fuse_stats_pair and cpg and cpg % 2 == 0
+        ok_single = (not pk.pair) and self.fuse_stats and (cpg in (1, 2, 4) or (cpg and cpg % 8 == 0))
+        if stats_groups and stats_groups <= 32 and (ok_pair or ok_single):
             stats = self._stats_slot(N, stats_groups, x.device)
             self._stats[id(y)] = (stats, stats_groups, y)     # holding y keeps its id unique until consumed
         if pk.pair:
