@@ -43,6 +43,15 @@ struct PairArgs {
     long long y_ld;
     double* gn_stats;
     int gn_cpg, gn_groups;
+    // GN_IN variant: the conv input is SiLU(GroupNorm(x)) applied on the fly by the operand producers
+    const __nv_bfloat16* x;      // raw (un-normalised) input, channels-last
+    long long x_ld;
+    int Cin;
+    const double* gi_stats;      // [N][FCWDM_GN_STAT_REPLICAS][gi_groups][2] statistics of x
+    const float* gi_gamma;
+    const float* gi_beta;
+    int gi_groups;
+    float gi_eps;
 };
 
 template <int N_TILE>
@@ -53,11 +62,11 @@ struct PairCfg {
     static constexpr int ROWP = 10, HROWS = 18;
     static constexpr int PLANE_BYTES = HROWS * ROWP * 128;    // 23040
     static constexpr int SLOT_BYTES = 23552;                  // 1024-aligned
-    static constexpr int A_SLOTS_RAW = (227 * 1024 - 3072 - B_BYTES) / SLOT_BYTES;
+    static constexpr int A_SLOTS_RAW = (227 * 1024 - 3584 - B_BYTES) / SLOT_BYTES;
     static constexpr int A_SLOTS = A_SLOTS_RAW > 6 ? 6 : A_SLOTS_RAW;
     static constexpr int RING = 6;
     static constexpr int TMEM_COLS = 8 * N_TILE < 32 ? 32 : 8 * N_TILE;
-    static constexpr int SMEM_BYTES = 1024 + B_BYTES + A_SLOTS * SLOT_BYTES + 2048;
+    static constexpr int SMEM_BYTES = 1024 + B_BYTES + A_SLOTS * SLOT_BYTES + 2048 + 512;
     static_assert(B_TAP_BYTES % 1024 == 0, "weight tiles must stay 1024-B aligned");
     static_assert(A_SLOTS >= 3, "not enough plane slots");
     static_assert(TMEM_COLS <= 512, "accumulator ring exceeds tensor memory");
@@ -138,10 +147,16 @@ __device__ __forceinline__ void p_flush_pair_stats(float* ps, float* pq, float* 
     for (int i = 0; i < P; ++i) ps[i] = pq[i] = 0.f;
 }
 
+__device__ __forceinline__ float p_silu(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return x * fmaf(0.5f, t, 0.5f);
+}
+
 constexpr int kPWarpProdA = 4, kPWarpProdB = 5, kPWarpAlloc = 6, kPWarpMma = 7;
 
-template <int N_TILE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+template <int N_TILE, bool GN_IN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1)
     conv3d_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const PairArgs args) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -156,10 +171,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     const uint32_t acc_full = empty_a + 8 * Cfg::A_SLOTS;           // [RING]     (each CTA, multicast commit)
     const uint32_t acc_empty = acc_full + 8 * Cfg::RING;            // [RING]     (leader; 8 remote warp arrivals)
     const uint32_t b_full = acc_empty + 8 * Cfg::RING;              // [1]        (leader)
-    const uint32_t tmem_slot = b_full + 8;
+    const uint32_t landed_a = b_full + 8;                           // [A_SLOTS]  (GN_IN: this CTA's raw plane landed)
+    const uint32_t tmem_slot = landed_a + 8 * Cfg::A_SLOTS;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* wstat = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));
     float* sbias = reinterpret_cast<float*>(smem_raw + (bars + 512 - smem_u32(smem_raw)));   // [N_TILE]
+    float* sgn = reinterpret_cast<float*>(smem_raw + (bars + 2048 - smem_u32(smem_raw)));    // [2][64] GN_IN scale / shift
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -170,8 +187,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::A_SLOTS; ++i) {
-            mbar_init(full_a + 8 * i, 1);
+            mbar_init(full_a + 8 * i, GN_IN ? 8 : 1);   // GN_IN: 4 producer warps x 2 CTAs arrive remotely
             mbar_init(empty_a + 8 * i, 1);
+            mbar_init(landed_a + 8 * i, 1);
         }
         for (int i = 0; i < Cfg::RING; ++i) {
             mbar_init(acc_full + 8 * i, 1);
@@ -202,6 +220,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         }
     } else if (warp == kPWarpProdA) {
         // ============ A producer: this CTA's halo planes, in the same order and slots as the peer's ============
+        // plain variant: completion bytes go straight to the leader's full_a barrier (MMA may start);
+        // GN_IN variant: they go to this CTA's own landed_a barrier; the transform warps below take it from there.
         if (lane == 0) {
             uint32_t J = 0;
             for (int item = cluster_id; item < args.num_items; item += num_clusters) {
@@ -209,10 +229,97 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
                 for (int k = 0; k < it.L + 2; ++k, ++J) {
                     const uint32_t slot = J % Cfg::A_SLOTS, use = J / Cfg::A_SLOTS;
                     mbar_wait(empty_a + 8 * slot, (use & 1) ^ 1);
-                    if (leader) mbar_arrive_expect_tx(full_a + 8 * slot, 2 * Cfg::PLANE_BYTES);
-                    tma_load_5d_2sm(smem_a + slot * Cfg::SLOT_BYTES, &map_a, full_a + 8 * slot, 0, it.w0 - 1, it.h0 - 1,
+                    if (GN_IN) {
+                        mbar_arrive_expect_tx(landed_a + 8 * slot, Cfg::PLANE_BYTES);
+                        tma_load_5d(smem_a + slot * Cfg::SLOT_BYTES, &map_a, landed_a + 8 * slot, 0, it.w0 - 1, it.h0 - 1,
                                     it.d_begin - 1 + k, it.n);
+                    } else {
+                        if (leader) mbar_arrive_expect_tx(full_a + 8 * slot, 2 * Cfg::PLANE_BYTES);
+                        tma_load_5d_2sm(smem_a + slot * Cfg::SLOT_BYTES, &map_a, full_a + 8 * slot, 0, it.w0 - 1,
+                                        it.h0 - 1, it.d_begin - 1 + k, it.n);
+                    }
                 }
+            }
+        }
+    } else if (GN_IN && warp >= 8) {
+        // ============ A producers with fused GroupNorm + SiLU (4 warps): global -> registers -> normalise, activate ->
+        // swizzled shared memory (the layout TMA SWIZZLE_128B would have produced).  Out-of-range halo voxels are
+        // written as ZERO: the convolution pads the ACTIVATED tensor.  ============
+        const int pt = threadIdx.x - 256;                       // 0..127
+        const uint32_t full_a_leader = mapa_u32(full_a, 0);
+        constexpr int CHUNKS = Cfg::HROWS * Cfg::ROWP * 8;       // 16-byte chunks per plane (1440)
+        constexpr int PER_THREAD = (CHUNKS + 127) / 128;         // 12
+        int cur_n = -1;
+        uint32_t J = 0;
+        for (int item = cluster_id; item < args.num_items; item += num_clusters) {
+            const PairItem it = decode_item(item, args, (int)rank);
+            if (it.n != cur_n) {
+                cur_n = it.n;
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (pt < 64) {
+                    float sc = 0.f, sh = 0.f;
+                    if (pt < args.Cin) {
+                        const int cpg = args.Cin / args.gi_groups;
+                        const int g = pt / cpg;
+                        double sum = 0.0, sq = 0.0;
+                        for (int r = 0; r < FCWDM_GN_STAT_REPLICAS; ++r) {
+                            const double* sp = args.gi_stats + (((long long)it.n * FCWDM_GN_STAT_REPLICAS + r) * args.gi_groups + g) * 2;
+                            sum += sp[0];
+                            sq += sp[1];
+                        }
+                        const double cnt = (double)args.D * args.H * args.W * cpg;
+                        const double mean = sum / cnt;
+                        double var = sq / cnt - mean * mean;
+                        var = var < 0.0 ? 0.0 : var;
+                        const float rstd = (float)(1.0 / sqrt(var + (double)args.gi_eps));
+                        sc = rstd * __ldg(args.gi_gamma + pt);
+                        sh = __ldg(args.gi_beta + pt) - (float)mean * sc;
+                    }
+                    sgn[pt] = sc;
+                    sgn[64 + pt] = sh;
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+            }
+            for (int k = 0; k < it.L + 2; ++k, ++J) {
+                const uint32_t slot = J % Cfg::A_SLOTS, use = J / Cfg::A_SLOTS;
+                const int d = it.d_begin - 1 + k;
+                const bool d_ok = (d >= 0) && (d < args.D);
+                mbar_wait(landed_a + 8 * slot, use & 1);          // TMA has written the raw plane (zeros out of range)
+                const uint32_t base = smem_a + slot * Cfg::SLOT_BYTES;
+                if (d_ok) {
+#pragma unroll 4
+                    for (int q = 0; q < PER_THREAD; ++q) {
+                        const int c = pt + q * 128;
+                        const int r = c >> 3, jp = c & 7;
+                        const int hr = r / Cfg::ROWP, wc = r - hr * Cfg::ROWP;
+                        const int h = it.h0 - 1 + hr, w = it.w0 - 1 + wc;
+                        // out-of-range halo voxels stay ZERO: the convolution pads the ACTIVATED tensor
+                        if ((c < CHUNKS) && (h >= 0) && (h < args.H) && (w >= 0) && (w < args.W)) {
+                            const int j = jp ^ (r & 7);            // logical 16-byte chunk = channels 8j .. 8j+7
+                            uint4 u;
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                         : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                                         : "r"(base + c * 16));
+                            float f[8];
+                            unpack8(u, f);
+                            const float4 s0 = *reinterpret_cast<const float4*>(sgn + j * 8);
+                            const float4 s1 = *reinterpret_cast<const float4*>(sgn + j * 8 + 4);
+                            const float4 t0 = *reinterpret_cast<const float4*>(sgn + 64 + j * 8);
+                            const float4 t1 = *reinterpret_cast<const float4*>(sgn + 64 + j * 8 + 4);
+                            f[0] = p_silu(fmaf(f[0], s0.x, t0.x)); f[1] = p_silu(fmaf(f[1], s0.y, t0.y));
+                            f[2] = p_silu(fmaf(f[2], s0.z, t0.z)); f[3] = p_silu(fmaf(f[3], s0.w, t0.w));
+                            f[4] = p_silu(fmaf(f[4], s1.x, t1.x)); f[5] = p_silu(fmaf(f[5], s1.y, t1.y));
+                            f[6] = p_silu(fmaf(f[6], s1.z, t1.z)); f[7] = p_silu(fmaf(f[7], s1.w, t1.w));
+                            const uint4 o = pack8(f);
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(base + c * 16), "r"(o.x),
+                                         "r"(o.y), "r"(o.z), "r"(o.w)
+                                         : "memory");
+                        }
+                    }
+                }
+                fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(full_a_leader + 8 * slot);
             }
         }
     } else if (warp == kPWarpMma) {
@@ -442,23 +549,29 @@ int conv3d_pair_init_device() {
                       "fcwdm_init: cuTensorMapEncodeTiled entry point not available (%s)", cudaGetErrorString(e));
         g_encode_p = reinterpret_cast<EncodeTiledFnP>(fn);
     }
-    cudaError_t e = cudaFuncSetAttribute(conv3d_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv3d_pair_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          PairCfg<64>::SMEM_BYTES);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(conv3d_pair_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(conv3d_pair_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 PairCfg<16>::SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv3d_pair_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 PairCfg<64>::SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv3d_pair_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  PairCfg<16>::SMEM_BYTES);
     FCWDM_REQUIRE(e == cudaSuccess, FCWDM_ERR_CUDA, "fcwdm_init: cudaFuncSetAttribute(pair) failed: %s",
                   cudaGetErrorString(e));
     return FCWDM_OK;
 }
 
-template <int N_TILE>
+template <int N_TILE, bool GN_IN>
 static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const PairArgs& a, cudaStream_t st) {
     const int clusters = num_sms() / 2;
     const int grid = 2 * (a.num_items < clusters ? a.num_items : clusters);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(GN_IN ? 384 : 256);
     cfg.dynamicSmemBytes = PairCfg<N_TILE>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -466,7 +579,7 @@ static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const PairA
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;            // the cluster shape is static (__cluster_dims__)
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3d_pair_kernel<N_TILE>, ma, mb, a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3d_pair_kernel<N_TILE, GN_IN>, ma, mb, a);
     FCWDM_REQUIRE(e == cudaSuccess, FCWDM_ERR_CUDA, "fcwdm_conv3d_pair_fwd: launch failed: %s", cudaGetErrorString(e));
     FCWDM_CHECK_LAUNCH("fcwdm_conv3d_pair_fwd");
     return FCWDM_OK;
@@ -499,8 +612,10 @@ extern "C" int fcwdm_conv3d_pair_pack_weights(const float* w, void* wp, int64_t 
 
 extern "C" int fcwdm_conv3d_pair_fwd(const void* x, int64_t x_ld, const void* wp, const float* bias,
                                      const float* chan_bias, int64_t cb_ld, const void* residual, int64_t res_ld, void* y,
-                                     int64_t y_ld, double* gn_stats, int64_t gn_groups, int64_t N, int64_t D, int64_t H,
-                                     int64_t W, int64_t Cin, int64_t Cout, void* stream) {
+                                     int64_t y_ld, double* gn_stats, int64_t gn_groups, const double* gn_in_stats,
+                                     const float* gn_in_gamma, const float* gn_in_beta, int64_t gn_in_groups,
+                                     float gn_in_eps, int64_t N, int64_t D, int64_t H, int64_t W, int64_t Cin,
+                                     int64_t Cout, void* stream) {
     FCWDM_REQUIRE(x && wp && y, FCWDM_ERR_INVALID, "fcwdm_conv3d_pair_fwd: null pointer");
     FCWDM_REQUIRE(fcwdm_conv3d_pair_supported(Cin, Cout, 3), FCWDM_ERR_UNSUPPORTED,
                   "fcwdm_conv3d_pair_fwd: needs C_in <= 64, C_out <= 64, C_out %% 8 == 0 (3x3x3)");
@@ -581,5 +696,14 @@ extern "C" int fcwdm_conv3d_pair_fwd(const void* x, int64_t x_ld, const void* wp
     a.gn_stats = gn_stats;
     a.gn_groups = gn_stats ? (int)gn_groups : 0;
     a.gn_cpg = gn_stats ? (int)(Cout / gn_groups) : 0;
-    return n_tile == 64 ? launch_pair<64>(ma, mb, a, (cudaStream_t)stream) : launch_pair<16>(ma, mb, a, (cudaStream_t)stream);
+    a.x = (const __nv_bfloat16*)x; a.x_ld = x_ld; a.Cin = (int)Cin;
+    a.gi_stats = gn_in_stats; a.gi_gamma = gn_in_gamma; a.gi_beta = gn_in_beta;
+    a.gi_groups = (int)gn_in_groups; a.gi_eps = gn_in_eps;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gn_in_stats != nullptr) {
+        FCWDM_REQUIRE(gn_in_gamma && gn_in_beta && gn_in_groups > 0 && Cin % gn_in_groups == 0, FCWDM_ERR_INVALID,
+                      "fcwdm_conv3d_pair_fwd: fused input GroupNorm needs gamma, beta and groups dividing C_in");
+        return n_tile == 64 ? launch_pair<64, true>(ma, mb, a, st) : launch_pair<16, true>(ma, mb, a, st);
+    }
+    return n_tile == 64 ? launch_pair<64, false>(ma, mb, a, st) : launch_pair<16, false>(ma, mb, a, st);
 }

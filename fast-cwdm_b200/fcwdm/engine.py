@@ -43,6 +43,7 @@ class WavUNetEngine:
         self.fuse_stats = os.environ.get("FCWDM_FUSED_STATS", "0") == "1"          # single-CTA kernel: opt-in
         self.fuse_stats_pair = os.environ.get("FCWDM_NO_FUSED_STATS_PAIR", "0") != "1"  # pair kernel: register sums, free
         self.use_pair = os.environ.get("FCWDM_NO_PAIR", "0") != "1"
+        self.fuse_gn_in = os.environ.get("FCWDM_NO_FUSED_GN_IN", "0") != "1"
 
     # ------------------------------------------------------------------ weights
     def _signature(self):
@@ -106,7 +107,7 @@ class WavUNetEngine:
             return torch.empty((rows, ld), dtype=torch.bfloat16, device=device)
         return torch.zeros((rows, ld), dtype=torch.bfloat16, device=device)   # pad channels feed zero weights
 
-    def _conv3d(self, mod, x, N, dims, chan_bias=None, residual=None, out_ld=None, stats_groups=0):
+    def _conv3d(self, mod, x, N, dims, chan_bias=None, residual=None, out_ld=None, stats_groups=0, gn_in=None):
         """stats_groups > 0: the conv epilogue also produces the GroupNorm statistics of its output (kept in
         self._stats under the output buffer's id until the consuming GroupNorm picks them up)."""
         pk = self._conv[id(mod)]
@@ -121,8 +122,10 @@ class WavUNetEngine:
             self._stats[id(y)] = (stats, stats_groups, y)     # holding y keeps its id unique until consumed
         if pk.pair:
             ops.conv3d_pair_cl(x, pk.wp, pk.bias, y, (N,) + tuple(dims), pk.cin, pk.cout, chan_bias=chan_bias,
-                               residual=residual, gn_stats=stats, gn_groups=stats_groups if stats is not None else 0)
+                               residual=residual, gn_stats=stats, gn_groups=stats_groups if stats is not None else 0,
+                               gn_in=gn_in)
         else:
+            assert gn_in is None
             ops.conv3d_cl(x, pk.wp, pk.bias, y, (N,) + tuple(dims), pk.cin, pk.cout, pk.k, chan_bias=chan_bias,
                           residual=residual, gn_stats=stats, gn_groups=stats_groups if stats is not None else 0)
         return y
@@ -137,18 +140,33 @@ class WavUNetEngine:
         self._arena_pos += n
         return out
 
+    def _take_stats(self, gn, x, N):
+        """(stats buffer, already_filled): statistics left by the producing conv's epilogue, or an empty buffer."""
+        pre = self._stats.pop(id(x), None)
+        if pre is not None and pre[1] == gn.num_groups and pre[2] is x:
+            return pre[0], True
+        return torch.empty((N, ops.GN_STAT_REPLICAS, gn.num_groups, 2), dtype=torch.float64, device=x.device), False
+
     def _gn_silu(self, gn, x, N, S, silu=True):
         C = gn.num_channels
         y = self._buf(N * S, C, x.device)
-        pre = self._stats.pop(id(x), None)
-        if pre is not None and pre[1] == gn.num_groups and pre[2] is x:
-            stats, have = pre[0], True
-        else:
-            stats, have = torch.empty((N, ops.GN_STAT_REPLICAS, gn.num_groups, 2), dtype=torch.float64,
-                                      device=x.device), False
+        stats, have = self._take_stats(gn, x, N)
         ops.groupnorm_silu(x, y, stats, self._p32(gn.weight), self._p32(gn.bias), N, S, C, gn.num_groups, gn.eps, silu,
                            have_stats=have)
         return y
+
+    def _gn_silu_conv(self, gn, x, mod, N, dims, **kw):
+        """conv(SiLU(GroupNorm(x))).  For the CTA-pair kernel the normalisation + activation run inside the conv's
+        operand producers (no GroupNorm-apply pass, no intermediate tensor); otherwise apply, then convolve."""
+        pk = self._conv[id(mod)]
+        S = dims[0] * dims[1] * dims[2]
+        if pk.pair and self.fuse_gn_in and gn.num_channels == pk.cin and pk.cin % gn.num_groups == 0:
+            stats, have = self._take_stats(gn, x, N)
+            if not have:
+                ops.groupnorm_stats(x, stats, N, S, pk.cin, gn.num_groups)
+            return self._conv3d(mod, x, N, dims, gn_in=(stats, self._p32(gn.weight), self._p32(gn.bias),
+                                                         gn.num_groups, gn.eps), **kw)
+        return self._conv3d(mod, self._gn_silu(gn, x, N, S), N, dims, **kw)
 
     def _emb_all(self, emb):
         out = torch.empty((emb.shape[0], self._emb_w.shape[0]), dtype=torch.float32, device=emb.device)
@@ -165,10 +183,10 @@ class WavUNetEngine:
         dev = x.device
         cin, cout = blk.channels, blk.out_channels
         emb_out = self._emb_out(blk, emb)
-        a = self._gn_silu(blk.in_layers[0], x, N, S)
+        gn1, conv1 = blk.in_layers[0], blk.in_layers[2]
         skip_out = skip
         if blk.down:
-            h_full = self._conv3d(blk.in_layers[2], a, N, dims)
+            h_full = self._gn_silu_conv(gn1, x, conv1, N, dims)
             d2 = (dims[0] // 2, dims[1] // 2, dims[2] // 2)
             s2 = d2[0] * d2[1] * d2[2]
             h = self._buf(N * s2, cout, dev)
@@ -182,7 +200,7 @@ class WavUNetEngine:
         elif blk.up:
             if skip is None:
                 raise FcwdmError("up-sampling ResBlock reached without stored high-frequency sub-bands")
-            h_low = self._conv3d(blk.in_layers[2], a, N, dims)
+            h_low = self._gn_silu_conv(gn1, x, conv1, N, dims)
             d2 = (dims[0] * 2, dims[1] * 2, dims[2] * 2)
             s2 = d2[0] * d2[1] * d2[2]
             h = self._buf(N * s2, cout, dev)
@@ -191,13 +209,12 @@ class WavUNetEngine:
             ops.idwt3d_cl(x, skip, (N,) + d2, cin, xu, bias=None, lll_scale=3.0)          # IDWT(3x, skip)
             x, dims, S, skip_out = xu, d2, s2, None
         else:
-            h = self._conv3d(blk.in_layers[2], a, N, dims, chan_bias=emb_out,             # conv + emb (:262)
-                             stats_groups=blk.out_layers[0].num_groups)
-        b = self._gn_silu(blk.out_layers[0], h, N, S)
+            h = self._gn_silu_conv(gn1, x, conv1, N, dims, chan_bias=emb_out,             # conv + emb (:262)
+                                   stats_groups=blk.out_layers[0].num_groups)
         if isinstance(blk.skip_connection, torch.nn.Conv3d):
             x = self._conv3d(blk.skip_connection, x, N, dims)
-        out = self._conv3d(blk.out_layers[3], b, N, dims, residual=x,                     # skip(x) + h (:266)
-                           stats_groups=self.model.num_groups)
+        out = self._gn_silu_conv(blk.out_layers[0], h, blk.out_layers[3], N, dims, residual=x,   # skip(x) + h (:266)
+                                 stats_groups=self.model.num_groups)
         return out, skip_out, dims
 
     # ------------------------------------------------------------------ whole network
@@ -267,9 +284,8 @@ class WavUNetEngine:
         for module in m.out_res:
             for layer in module:
                 h, _, hdims = self._resblock(layer, h, None, emb, N, hdims)
-        S = hdims[0] * hdims[1] * hdims[2]
-        a = self._gn_silu(m.out[0], h, N, S)
-        return self._conv3d(m.out[2], a, N, hdims, out_ld=out_ld or max(8, (m.out_channels + 7) // 8 * 8))
+        return self._gn_silu_conv(m.out[0], h, m.out[2], N, hdims,
+                                  out_ld=out_ld or max(8, (m.out_channels + 7) // 8 * 8))
 
     def forward(self, x, timesteps):
         """Planar fp32 API of the reference: x (N, C, D, H, W), timesteps (N,) -> (N, out_channels, D, H, W)."""

@@ -44,8 +44,8 @@ PROTOTYPES = {
     "fcwdm_conv3d_pair_supported": (_c_int, [_c_i64, _c_i64, _c_int]),
     "fcwdm_conv3d_pair_packed_elems": (_c_i64, [_c_i64, _c_i64]),
     "fcwdm_conv3d_pair_pack_weights": (_c_int, [_c_p, _c_p, _c_i64, _c_i64, _c_p]),
-    "fcwdm_conv3d_pair_fwd": (_c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64]
-                             + [_c_i64] * 6 + [_c_p]),
+    "fcwdm_conv3d_pair_fwd": (_c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64,
+                                       _c_p, _c_p, _c_p, _c_i64, _c_f] + [_c_i64] * 6 + [_c_p]),
 }
 
 FCWDM_F32, FCWDM_BF16 = 0, 1

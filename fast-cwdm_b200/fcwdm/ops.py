@@ -185,6 +185,11 @@ def groupnorm_silu(x, y, stats, gamma, beta, N, S, C, G, eps=1e-5, silu=True, ha
                     _ptr(beta), N, S, C, G, float(eps), 1 if silu else 0, st)
 
 
+def groupnorm_stats(x, stats, N, S, C, G):
+    with _on(x.device) as st:
+        native.call("fcwdm_groupnorm_stats", _ptr(x), x.stride(0), _ptr(stats), N, S, C, G, st)
+
+
 def timestep_embedding(t, out, dim, max_period=10000.0):
     with _on(t.device) as st:
         native.call("fcwdm_timestep_embedding", _ptr(t), _ptr(out), t.shape[0], dim, float(max_period), st)
@@ -238,13 +243,18 @@ def conv3d_pair_pack_weights(w):
     return wp
 
 
-def conv3d_pair_cl(x, wp, bias, y, dims, cin, cout, chan_bias=None, residual=None, gn_stats=None, gn_groups=0):
-    """kd-fused two-CTA conv (3x3x3, C_in <= 64, C_out <= 64); same arguments as conv3d_cl."""
+def conv3d_pair_cl(x, wp, bias, y, dims, cin, cout, chan_bias=None, residual=None, gn_stats=None, gn_groups=0,
+                   gn_in=None):
+    """kd-fused two-CTA conv (3x3x3, C_in <= 64, C_out <= 64); same arguments as conv3d_cl.
+    gn_in = (stats, gamma, beta, groups, eps): convolve SiLU(GroupNorm(x)) with the normalisation fused into the
+    operand producers (x is then the raw tensor)."""
     N, D, H, W = dims
     with _on(x.device) as st:
         native.call("fcwdm_conv3d_pair_fwd", _ptr(x), x.stride(0), _ptr(wp), _ptr(bias), _ptr(chan_bias),
                     chan_bias.stride(0) if chan_bias is not None else 0, _ptr(residual),
                     residual.stride(0) if residual is not None else 0, _ptr(y), y.stride(0), _ptr(gn_stats), gn_groups,
+                    _ptr(gn_in[0]) if gn_in else _VP(None), _ptr(gn_in[1]) if gn_in else _VP(None),
+                    _ptr(gn_in[2]) if gn_in else _VP(None), gn_in[3] if gn_in else 0, float(gn_in[4]) if gn_in else 0.0,
                     N, D, H, W, cin, cout, st)
 
 

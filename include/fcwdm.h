@@ -178,14 +178,19 @@ int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, const float* b
  * two-CTA (cta_group::2) implicit GEMM with the weights resident in the CTA pair's shared memory
  * (csrc/conv3d_pair.cu).  Same semantics and epilogue options as fcwdm_conv3d_fwd; its own weight packing
  * [kh*3+kw][kd][C_out_p][64] (C_out_p = 16 or 64).  x must expose 64 readable channels per voxel (x_ld >= 64).
+ * gn_in_stats (optional): x is the RAW tensor and the kernel convolves SiLU(GroupNorm(x)) instead, normalising and
+ * activating in its operand producers from the statistics [N][FCWDM_GN_STAT_REPLICAS][gn_in_groups][2] of x
+ * (as written by fcwdm_groupnorm_stats or a producing conv's gn_stats) and gamma/beta[C_in] -- the GroupNorm-apply
+ * pass and its intermediate tensor (nn.py:17-19 + nn.SiLU, wunet.py:186-187,210-211,702-703) disappear.
  * ---------------------------------------------------------------------------------------------------- */
 int fcwdm_conv3d_pair_supported(int64_t Cin, int64_t Cout, int ksize);
 int64_t fcwdm_conv3d_pair_packed_elems(int64_t Cout, int64_t Cin);
 int fcwdm_conv3d_pair_pack_weights(const float* w, void* wp, int64_t Cout, int64_t Cin, void* stream);
 int fcwdm_conv3d_pair_fwd(const void* x, int64_t x_ld, const void* wp, const float* bias, const float* chan_bias,
                           int64_t cb_ld, const void* residual, int64_t res_ld, void* y, int64_t y_ld,
-                          double* gn_stats, int64_t gn_groups, int64_t N, int64_t D, int64_t H, int64_t W,
-                          int64_t Cin, int64_t Cout, void* stream);
+                          double* gn_stats, int64_t gn_groups, const double* gn_in_stats, const float* gn_in_gamma,
+                          const float* gn_in_beta, int64_t gn_in_groups, float gn_in_eps, int64_t N, int64_t D,
+                          int64_t H, int64_t W, int64_t Cin, int64_t Cout, void* stream);
 
 #ifdef __cplusplus
 }

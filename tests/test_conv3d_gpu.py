@@ -165,3 +165,32 @@ def test_conv3d_pair_epilogue_and_stats():
 def test_conv3d_pair_full_resolution():
     got, ref, _ = run_pair(1, 112, 112, 80, 64, 64, seed=9)
     check(got, ref)
+
+
+@pytest.mark.parametrize("case", [(1, 6, 20, 16, 64, 64), (2, 9, 18, 10, 32, 64), (1, 23, 40, 24, 64, 8)])
+def test_conv3d_pair_fused_input_groupnorm(case):
+    """conv(SiLU(GroupNorm(x))) with the normalisation applied inside the conv's operand producers."""
+    from fcwdm import native, ops
+    from gpu_util import bf16_round, from_cl, to_cl
+    N, D, H, W, cin, cout = case
+    G = 32
+    g = torch.Generator().manual_seed(11)
+    x = bf16_round(torch.randn(N, cin, D, H, W, generator=g) * 1.5 + 0.3).cuda()
+    w = bf16_round(torch.randn(cout, cin, 3, 3, 3, generator=g) / np.sqrt(cin * 27)).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    gamma = (1 + 0.2 * torch.randn(cin, generator=g)).cuda()
+    beta = (0.2 * torch.randn(cin, generator=g)).cuda()
+    xc = to_cl(x)
+    S = D * H * W
+    stats = torch.empty((N, ops.GN_STAT_REPLICAS, G, 2), dtype=torch.float64, device="cuda")
+    with ops._on(x.device) as st:
+        native.call("fcwdm_groupnorm_stats", ops._ptr(xc), xc.stride(0), ops._ptr(stats), N, S, cin, G, st)
+    wp = ops.conv3d_pair_pack_weights(w)
+    yc = torch.zeros((N * S, 64), dtype=torch.bfloat16, device="cuda")
+    ops.conv3d_pair_cl(xc, wp, bias, yc, (N, D, H, W), cin, cout, gn_in=(stats, gamma, beta, G, 1e-5))
+    torch.cuda.synchronize()
+    got = from_cl(yc, (N, cout, D, H, W))
+    a = bf16_round(F.silu(F.group_norm(x, G, gamma, beta, 1e-5)))
+    ref = F.conv3d(a, w, bias, padding=1)
+    err = float((got - ref).abs().max())
+    assert err <= 2e-2 * float(ref.abs().max()) + 2e-3, err

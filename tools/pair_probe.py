@@ -34,3 +34,28 @@ for name, wp, fn in (("pair", ops.conv3d_pair_pack_weights(w), ops.conv3d_pair_c
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     print(f"{name:6s} conv {D}x{H}x{W} {ci}->{co}: {ms*1e3:.1f} us {2.0*S*ci*co*27/ms/1e9:.1f} TFLOP/s", flush=True)
+
+# fused input GroupNorm variant
+G = 32
+stats = torch.empty((1, ops.GN_STAT_REPLICAS, G, 2), dtype=torch.float64, device=dev)
+ops.groupnorm_stats(x, stats, 1, S, 64, G)
+gamma = torch.ones(64, device=dev)
+beta = torch.zeros(64, device=dev)
+wp = ops.conv3d_pair_pack_weights(w)
+ostats = torch.zeros((1, ops.GN_STAT_REPLICAS, G, 2), dtype=torch.float64, device=dev)
+for name, kw in (("pair+gn_in", dict(gn_in=(stats, gamma, beta, G, 1e-5))),
+                 ("pair+gn_in+stats", dict(gn_in=(stats, gamma, beta, G, 1e-5), gn_stats=ostats, gn_groups=G) if co == 64 else None),
+                 ("pair+stats", dict(gn_stats=ostats, gn_groups=G) if co == 64 else None)):
+    if kw is None:
+        continue
+    for _ in range(3):
+        ops.conv3d_pair_cl(x, wp, b, y, (1, D, H, W), ci, co, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ops.conv3d_pair_cl(x, wp, b, y, (1, D, H, W), ci, co, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    print(f"{name:18s} conv {D}x{H}x{W} {ci}->{co}: {ms*1e3:.1f} us {2.0*S*ci*co*27/ms/1e9:.1f} TFLOP/s", flush=True)
