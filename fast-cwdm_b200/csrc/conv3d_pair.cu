@@ -249,6 +249,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
         const uint32_t full_a_leader = mapa_u32(full_a, 0);
         constexpr int CHUNKS = Cfg::HROWS * Cfg::ROWP * 8;       // 16-byte chunks per plane (1440)
         constexpr int PER_THREAD = (CHUNKS + 127) / 128;         // 12
+        const int jmine = (pt & 7) ^ ((pt >> 3) & 7);
+        float sc[8], sh[8];
         int cur_n = -1;
         uint32_t J = 0;
         for (int item = cluster_id; item < args.num_items; item += num_clusters) {
@@ -257,7 +259,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
                 cur_n = it.n;
                 asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (pt < 64) {
-                    float sc = 0.f, sh = 0.f;
+                    float sc0 = 0.f, sh0 = 0.f;
                     if (pt < args.Cin) {
                         const int cpg = args.Cin / args.gi_groups;
                         const int g = pt / cpg;
@@ -272,13 +274,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
                         double var = sq / cnt - mean * mean;
                         var = var < 0.0 ? 0.0 : var;
                         const float rstd = (float)(1.0 / sqrt(var + (double)args.gi_eps));
-                        sc = rstd * __ldg(args.gi_gamma + pt);
-                        sh = __ldg(args.gi_beta + pt) - (float)mean * sc;
+                        sc0 = rstd * __ldg(args.gi_gamma + pt);
+                        sh0 = __ldg(args.gi_beta + pt) - (float)mean * sc0;
                     }
-                    sgn[pt] = sc;
-                    sgn[64 + pt] = sh;
+                    sgn[pt] = sc0;
+                    sgn[64 + pt] = sh0;
                 }
                 asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    sc[e] = sgn[jmine * 8 + e];
+                    sh[e] = sgn[64 + jmine * 8 + e];
+                }
             }
             for (int k = 0; k < it.L + 2; ++k, ++J) {
                 const uint32_t slot = J % Cfg::A_SLOTS, use = J / Cfg::A_SLOTS;
@@ -287,34 +294,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
                 mbar_wait(landed_a + 8 * slot, use & 1);          // TMA has written the raw plane (zeros out of range)
                 const uint32_t base = smem_a + slot * Cfg::SLOT_BYTES;
                 if (d_ok) {
-#pragma unroll 4
+                    // all shared-memory loads first (independent, pipelined), then the arithmetic and the stores:
+                    // a load -> compute -> store chain per chunk is latency-bound (~450 cycles per chunk)
+                    uint4* plane = reinterpret_cast<uint4*>(smem_raw + (base - smem_u32(smem_raw)));
+                    uint4 raw[PER_THREAD];
+                    uint32_t valid = 0;
+#pragma unroll
                     for (int q = 0; q < PER_THREAD; ++q) {
                         const int c = pt + q * 128;
-                        const int r = c >> 3, jp = c & 7;
+                        const int r = c >> 3;
                         const int hr = r / Cfg::ROWP, wc = r - hr * Cfg::ROWP;
                         const int h = it.h0 - 1 + hr, w = it.w0 - 1 + wc;
                         // out-of-range halo voxels stay ZERO: the convolution pads the ACTIVATED tensor
-                        if ((c < CHUNKS) && (h >= 0) && (h < args.H) && (w >= 0) && (w < args.W)) {
-                            const int j = jp ^ (r & 7);            // logical 16-byte chunk = channels 8j .. 8j+7
-                            uint4 u;
-                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                         : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
-                                         : "r"(base + c * 16));
-                            float f[8];
-                            unpack8(u, f);
-                            const float4 s0 = *reinterpret_cast<const float4*>(sgn + j * 8);
-                            const float4 s1 = *reinterpret_cast<const float4*>(sgn + j * 8 + 4);
-                            const float4 t0 = *reinterpret_cast<const float4*>(sgn + 64 + j * 8);
-                            const float4 t1 = *reinterpret_cast<const float4*>(sgn + 64 + j * 8 + 4);
-                            f[0] = p_silu(fmaf(f[0], s0.x, t0.x)); f[1] = p_silu(fmaf(f[1], s0.y, t0.y));
-                            f[2] = p_silu(fmaf(f[2], s0.z, t0.z)); f[3] = p_silu(fmaf(f[3], s0.w, t0.w));
-                            f[4] = p_silu(fmaf(f[4], s1.x, t1.x)); f[5] = p_silu(fmaf(f[5], s1.y, t1.y));
-                            f[6] = p_silu(fmaf(f[6], s1.z, t1.z)); f[7] = p_silu(fmaf(f[7], s1.w, t1.w));
-                            const uint4 o = pack8(f);
-                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(base + c * 16), "r"(o.x),
-                                         "r"(o.y), "r"(o.z), "r"(o.w)
-                                         : "memory");
+                        const bool in = (c < CHUNKS) && (h >= 0) && (h < args.H) && (w >= 0) && (w < args.W);
+                        raw[q] = make_uint4(0u, 0u, 0u, 0u);
+                        if (in) {
+                            raw[q] = plane[c];
+                            valid |= 1u << q;
                         }
+                    }
+                    // this thread's logical 16-byte chunk index is the same for all of its chunks
+                    // (c = pt + 128 q  =>  (c & 7) ^ ((c >> 3) & 7) does not depend on q): scale / shift live in registers
+#pragma unroll
+                    for (int q = 0; q < PER_THREAD; ++q) {
+                        float f[8];
+                        unpack8(raw[q], f);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = p_silu(fmaf(f[e], sc[e], sh[e]));
+                        if (valid & (1u << q)) plane[pt + q * 128] = pack8(f);
                     }
                 }
                 fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
