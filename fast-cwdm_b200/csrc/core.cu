@@ -18,6 +18,7 @@ void set_error(const char* fmt, ...) {
 
 int conv3d_init_device();       // conv3d.cu
 int conv3d_pair_init_device();  // conv3d_pair.cu
+int conv3d_wgrad_init_device(); // conv3d_wgrad.cu
 
 bool pdl_enabled() {
     static int v = -1;
@@ -46,5 +47,7 @@ extern "C" int fcwdm_init(int device) {
                   minor);
     int rc = fcwdm::conv3d_init_device();
     if (rc) return rc;
-    return fcwdm::conv3d_pair_init_device();
+    rc = fcwdm::conv3d_pair_init_device();
+    if (rc) return rc;
+    return fcwdm::conv3d_wgrad_init_device();
 }

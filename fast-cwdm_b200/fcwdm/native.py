@@ -46,6 +46,19 @@ PROTOTYPES = {
     "fcwdm_conv3d_pair_pack_weights": (_c_int, [_c_p, _c_p, _c_i64, _c_i64, _c_p]),
     "fcwdm_conv3d_pair_fwd": (_c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64,
                                        _c_p, _c_p, _c_p, _c_i64, _c_f] + [_c_i64] * 6 + [_c_p]),
+    "fcwdm_conv3d_wgrad_workspace_bytes": (_c_i64, [_c_i64] * 6 + [_c_int]),
+    "fcwdm_conv3d_wgrad": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_i64, _c_int] + [_c_i64] * 6 + [_c_int, _c_p]),
+    "fcwdm_conv3d_transpose_flip_weights": (_c_int, [_c_p, _c_p, _c_i64, _c_i64, _c_int, _c_p]),
+    "fcwdm_groupnorm_bwd": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p,
+                                     _c_p] + [_c_i64] * 4 + [_c_f, _c_int, _c_p]),
+    "fcwdm_colsum_cl": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_i64, _c_p]),
+    "fcwdm_dwt3d_cl_bwd": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_p, _c_i64, _c_p, _c_i64] + [_c_i64] * 5
+                           + [_c_f, _c_f, _c_p]),
+    "fcwdm_idwt3d_cl_bwd": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_int] + [_c_i64] * 5
+                            + [_c_f, _c_p]),
+    "fcwdm_add_cl": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_i64, _c_p]),
+    "fcwdm_linear_bwd": (_c_int, [_c_p, _c_p, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_p]),
+    "fcwdm_adamw": (_c_int, [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_f, _c_i64, _c_f, _c_p]),
 }
 
 FCWDM_F32, FCWDM_BF16 = 0, 1

@@ -307,3 +307,98 @@ def sample_to_image(sample, cond_1=None):
     with _on(sample.device) as st:
         native.call("fcwdm_sample_to_image", _ptr(sample), _ptr(cond_1), _ptr(img), N, d, h, w, st)
     return img
+
+
+# ----------------------------------------------------------------------------------------------------
+# training path: backward kernels (csrc/conv3d_wgrad.cu, csrc/train.cu)
+# ----------------------------------------------------------------------------------------------------
+_wgrad_ws = {}
+
+
+def _wgrad_workspace(nbytes, device):
+    """One grow-only scratch buffer per device for the wgrad split partial sums (stream-ordered reuse)."""
+    ws = _wgrad_ws.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _wgrad_ws[device] = ws
+    return ws
+
+
+def conv3d_wgrad(x, dy, dw, dims, cin, cout, k, accumulate=True):
+    """dw (Cout, Cin, k, k, k) f32 (+)= sum_v dy[v] (x) x[v + tap].  x: the conv's input (voxels, x_ld) cl bf16,
+    dy: gradient of its output (voxels, dy_ld >= round_up(Cout, 64)) cl bf16."""
+    N, D, H, W = dims
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == cout * cin * k ** 3
+    nbytes = native.load().fcwdm_conv3d_wgrad_workspace_bytes(N, D, H, W, cin, cout, k)
+    if nbytes < 0:
+        raise FcwdmError("conv3d_wgrad: bad shape")
+    ws = _wgrad_workspace(nbytes, x.device)
+    with _on(x.device) as st:
+        native.call("fcwdm_conv3d_wgrad", _ptr(x), x.stride(0), _ptr(dy), dy.stride(0), _ptr(dw), _ptr(ws), ws.numel(),
+                    1 if accumulate else 0, N, D, H, W, cin, cout, k, st)
+
+
+def conv3d_transpose_flip_weights(w):
+    """(Cout, Cin, k, k, k) f32 -> (Cin, Cout, k, k, k) f32 with reversed taps: the data-gradient conv's weights."""
+    _need_cuda(w, "conv3d_transpose_flip_weights")
+    cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+    w = w.detach().float().contiguous()
+    wt = torch.empty((cin, cout, k, k, k), dtype=torch.float32, device=w.device)
+    with _on(w.device) as st:
+        native.call("fcwdm_conv3d_transpose_flip_weights", _ptr(w), _ptr(wt), cout, cin, k, st)
+    return wt
+
+
+def groupnorm_bwd(x, dy, stats, gamma, beta, dx, dgamma, dbeta, N, S, C, G, eps=1e-5, silu=True, acc=None):
+    sums = torch.empty((N, GN_STAT_REPLICAS, C, 2), dtype=torch.float64, device=x.device)
+    with _on(x.device) as st:
+        native.call("fcwdm_groupnorm_bwd", _ptr(x), x.stride(0), _ptr(dy), dy.stride(0), _ptr(stats), _ptr(gamma),
+                    _ptr(beta), _ptr(sums), _ptr(acc), acc.stride(0) if acc is not None else 0, _ptr(dx), dx.stride(0),
+                    _ptr(dgamma), _ptr(dbeta), N, S, C, G, float(eps), 1 if silu else 0, st)
+
+
+def colsum_cl(x, N, S, C, out_sample=None, out_total=None):
+    with _on(x.device) as st:
+        native.call("fcwdm_colsum_cl", _ptr(x), x.stride(0), _ptr(out_sample),
+                    out_sample.stride(0) if out_sample is not None else 0, _ptr(out_total), N, S, C, st)
+
+
+def dwt3d_cl_bwd(dlll, dhi, dims, C, dx, acc=None, lll_scale=1.0 / 3.0, hi_scale=1.0, hi_sb=None):
+    """Adjoint of dwt3d_cl.  dims = (N, D, H, W) of dx (the DWT's input)."""
+    N, D, H, W = dims
+    with _on(dx.device) as st:
+        native.call("fcwdm_dwt3d_cl_bwd", _ptr(dlll), dlll.stride(0), _ptr(dhi), dhi.stride(-2) if dhi is not None else 0,
+                    (hi_sb if hi_sb is not None else (dhi.stride(0) if dhi is not None else 0)), _ptr(acc),
+                    acc.stride(0) if acc is not None else 0, _ptr(dx), dx.stride(0), N, D, H, W, C, float(lll_scale),
+                    float(hi_scale), st)
+
+
+def idwt3d_cl_bwd(dy, dims, C, dlll, dhi, lll_acc=None, hi_accumulate=False, lll_scale=3.0):
+    """Adjoint of idwt3d_cl.  dims = (N, D, H, W) of dy (the IDWT's output)."""
+    N, D, H, W = dims
+    with _on(dy.device) as st:
+        native.call("fcwdm_idwt3d_cl_bwd", _ptr(dy), dy.stride(0), _ptr(lll_acc),
+                    lll_acc.stride(0) if lll_acc is not None else 0, _ptr(dlll), dlll.stride(0) if dlll is not None else 0,
+                    _ptr(dhi), dhi.stride(-2) if dhi is not None else 0, dhi.stride(0) if dhi is not None else 0,
+                    1 if hi_accumulate else 0, N, D, H, W, C, float(lll_scale), st)
+
+
+def add_cl(a, b, y, rows, C):
+    with _on(a.device) as st:
+        native.call("fcwdm_add_cl", _ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(y), y.stride(0), rows, C, st)
+
+
+def linear_bwd(x, W, dy, dx=None, dW=None, db=None, act_in=0, accumulate_dx=False):
+    N, K = x.shape
+    M = dy.shape[1]
+    with _on(x.device) as st:
+        native.call("fcwdm_linear_bwd", _ptr(x), _ptr(W), _ptr(dy), dy.stride(0), _ptr(dx), _ptr(dW), _ptr(db), N, K, M,
+                    act_in, 1 if accumulate_dx else 0, st)
+
+
+def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    """One fused AdamW step over flat fp32 tensors (in place on p, m, v)."""
+    _need_cuda(p, "adamw")
+    with _on(p.device) as st:
+        native.call("fcwdm_adamw", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
+                    float(eps), float(weight_decay), int(step), float(grad_scale), st)

@@ -1,0 +1,439 @@
+"""Training execution of the wavelet U-Net denoiser on fcwdm kernels: forward with a tape, explicit backward.
+
+The reference trains ``WavUNetModel`` through autograd (scripts/train.py -> TrainLoop.forward_backward,
+guided_diffusion/train_util.py:396-460): cuDNN dgrad/wgrad for every nn.Conv3d, native GroupNorm / SiLU backward,
+the matmul chains of DWT_IDWT_Functions.py:139-156,184-208 for the wavelet up/down-sampling.  Here the forward is
+the same launch sequence as ``WavUNetEngine`` (GroupNorm-apply materialised, because its output is the wgrad
+operand) and records one closure per launch; the backward replays the closures in reverse, each a C-ABI launch:
+
+    conv3d  ->  dX: the forward tcgen05 kernel on dY with transposed, tap-reversed weights (gradient fan-in fused as
+                its residual add);  dW: fcwdm_conv3d_wgrad (tcgen05, MN-major operands);  db / d(timestep
+                embedding): fcwdm_colsum_cl
+    GroupNorm+SiLU -> fcwdm_groupnorm_bwd;   Haar DWT / IDWT -> their adjoints;   Linear -> fcwdm_linear_bwd
+
+Activation gradients are channels-last bf16; parameter gradients are fp32 views into ONE flat buffer laid out in
+``model.parameters()`` order (what the bucketed NCCL all-reduce of fcwdm.ddp and the fused AdamW of fcwdm.optim
+operate on).  Weight-tied ResBlocks accumulate both uses into the same slice.
+"""
+import torch
+
+from . import ops
+from .engine import WavUNetEngine, _ld, _Packed
+from .native import FcwdmError
+
+
+class WavUNetTrainEngine(WavUNetEngine):
+    def __init__(self, model):
+        super().__init__(model)
+        self._tsig = None
+        self._conv_t = {}
+        self._gflat = None
+        self._gview = {}
+        self._tape = []
+        self._grads = {}
+        self._keep = []
+        self.grad_ready_hook = None      # callable(lo, hi): flat-gradient range [lo, hi) is final (fcwdm.ddp)
+
+    # ------------------------------------------------------------------ parameters / gradients
+    def flat_grad(self, device):
+        params = list(self.model.parameters())
+        total = sum((p.numel() + 3) // 4 * 4 for p in params)
+        if self._gflat is None or self._gflat.device != device or self._gflat.numel() != total:
+            self._gflat = torch.zeros(total, dtype=torch.float32, device=device)
+            self._gview, self._goff, off = {}, {}, 0
+            for p in params:
+                self._gview[id(p)] = self._gflat[off:off + p.numel()].view(p.shape)
+                self._goff[id(p)] = (off, off + p.numel())
+                off += (p.numel() + 3) // 4 * 4          # 16-byte aligned slices
+        return self._gflat
+
+    def _gp(self, p):
+        return self._gview[id(p)]
+
+    def prepare_train(self, device):
+        self.prepare(device)
+        if self._tsig == self._sig:
+            return
+        self._conv_t.clear()
+        for mod in self.model.modules():
+            if isinstance(mod, torch.nn.Conv3d):
+                k = mod.kernel_size[0]
+                if mod.in_channels % 8:
+                    continue                                   # the stem conv: its input gradient is never needed
+                wt = ops.conv3d_transpose_flip_weights(mod.weight)
+                pk = _Packed()
+                pk.cin, pk.cout, pk.k = mod.out_channels, mod.in_channels, k
+                pk.pair = self.use_pair and ops.conv3d_pair_supported(pk.cin, pk.cout, k)
+                pk.wp = ops.conv3d_pair_pack_weights(wt) if pk.pair else ops.conv3d_pack_weights(wt)
+                pk.bias = None
+                self._conv_t[id(mod)] = pk
+        self._tsig = self._sig
+
+    # ------------------------------------------------------------------ gradient bookkeeping
+    def _take(self, t):
+        return self._grads.pop(id(t), None)
+
+    def _partial(self, t):
+        return self._grads.get(id(t))
+
+    def _set(self, t, g):
+        self._grads[id(t)] = g
+
+    def _pass(self, t, g, rows, C):
+        """Identity edge: d(t) += g."""
+        cur = self._grads.get(id(t))
+        if cur is None:
+            self._grads[id(t)] = g
+        else:
+            out = torch.empty((rows, _ld(C)), dtype=torch.bfloat16, device=g.device)
+            ops.add_cl(cur, g, out, rows, C)
+            self._grads[id(t)] = out
+
+    def _zeros_like_grad(self, rows, C, device):
+        return torch.zeros((rows, _ld(C)), dtype=torch.bfloat16, device=device)
+
+    # ------------------------------------------------------------------ taped building blocks
+    def _conv3d_t(self, mod, x, N, dims, emb=None, residual=None, out_ld=None, stats_groups=0, need_dx=True):
+        """emb = (d_emb_all, off, n, emb_slice): the timestep-embedding add fused in the conv epilogue."""
+        pk = self._conv[id(mod)]
+        rows = N * dims[0] * dims[1] * dims[2]
+        y = self._conv3d(mod, x, N, dims, chan_bias=emb[3] if emb else None, residual=residual, out_ld=out_ld,
+                         stats_groups=stats_groups)
+        self._keep.append((x, y, residual))
+        dims4 = (N,) + tuple(dims)
+
+        def bwd():
+            dy = self._take(y)
+            if dy is None:
+                return
+            if residual is not None:
+                self._pass(residual, dy, rows, pk.cout)
+            # bias gradient (+ per-sample timestep-embedding gradient) from one pass over dY
+            cs = _ld(pk.cout) if pk.cout % 8 else pk.cout
+            db = self._gp(mod.bias) if mod.bias is not None else None
+            if emb is not None or db is not None:
+                if pk.cout % 8:
+                    raise FcwdmError("conv3d backward: C_out must be a multiple of 8")
+                ops.colsum_cl(dy, N, rows // N, cs, out_sample=emb[0][:, emb[1]:emb[1] + emb[2]] if emb else None,
+                              out_total=db)
+            ops.conv3d_wgrad(x, dy, self._gp(mod.weight), dims4, pk.cin, pk.cout, pk.k, accumulate=True)
+            if need_dx:
+                pt = self._conv_t[id(mod)]
+                dx = torch.empty((rows, _ld(pk.cin)), dtype=torch.bfloat16, device=dy.device)
+                acc = self._partial(x)
+                if pt.pair:
+                    ops.conv3d_pair_cl(dy, pt.wp, None, dx, dims4, pt.cin, pt.cout, residual=acc)
+                else:
+                    ops.conv3d_cl(dy, pt.wp, None, dx, dims4, pt.cin, pt.cout, pt.k, residual=acc)
+                self._set(x, dx)
+            self._param_done(mod.weight, mod.bias)
+
+        self._tape.append(bwd)
+        return y
+
+    def _gn_silu_t(self, gn, x, N, S, silu=True):
+        C = gn.num_channels
+        y = self._buf(N * S, C, x.device)
+        stats, have = self._take_stats(gn, x, N)
+        gamma, beta = self._p32(gn.weight), self._p32(gn.bias)
+        ops.groupnorm_silu(x, y, stats, gamma, beta, N, S, C, gn.num_groups, gn.eps, silu, have_stats=have)
+        self._keep.append((x, y))
+
+        def bwd():
+            dy = self._take(y)
+            if dy is None:
+                return
+            dx = torch.empty((N * S, _ld(C)), dtype=torch.bfloat16, device=x.device)
+            ops.groupnorm_bwd(x, dy, stats, gamma, beta, dx, self._gp(gn.weight), self._gp(gn.bias), N, S, C,
+                              gn.num_groups, gn.eps, silu, acc=self._partial(x))
+            self._set(x, dx)
+            self._param_done(gn.weight, gn.bias)
+
+        self._tape.append(bwd)
+        return y
+
+    def _gn_silu_conv(self, gn, x, mod, N, dims, **kw):       # training: GroupNorm output materialised (wgrad operand)
+        S = dims[0] * dims[1] * dims[2]
+        return self._conv3d_t(mod, self._gn_silu_t(gn, x, N, S), N, dims, **kw)
+
+    def _param_done(self, *params):
+        if self.grad_ready_hook is not None:
+            for p in params:
+                if p is not None:
+                    self._uses_left[id(p)] -= 1
+                    if self._uses_left[id(p)] == 0:
+                        self.grad_ready_hook(*self._goff[id(p)])
+
+    def _emb_slice(self, blk, emb_all, d_emb_all):
+        off, n = self._emb_off[id(blk)]
+        return (d_emb_all, off, n, emb_all[:, off:off + n])
+
+    def _dwt_t(self, x, dims4, C, lll, hi, emb=None, lll_scale=1.0 / 3.0, hi_scale=1.0, hi_sb=None, need_dx=True):
+        N, D, H, W = dims4
+        ops.dwt3d_cl(x, dims4, C, lll, hi, lll_bias=emb[3] if emb else None, lll_scale=lll_scale, hi_scale=hi_scale,
+                     hi_sb=hi_sb)
+        self._keep.append((x, lll, hi))
+        rows2 = N * (D // 2) * (H // 2) * (W // 2)
+        # the concatenated WaveletDownsample output is ONE tensor (lll and hi are views of it): key on its base
+        key_l = lll._base if (hi_sb is not None and lll._base is not None) else lll
+
+        def bwd():
+            if hi_sb is not None:
+                dcat = self._take(key_l)
+                if dcat is None:
+                    return
+                dl, dh = dcat[:, :C], dcat[:, C:]
+            else:
+                dl = self._take(lll)
+                dh = self._take(hi) if hi is not None else None
+                if dl is None and dh is None:
+                    return
+                if dl is None:
+                    dl = self._zeros_like_grad(rows2, C, x.device)
+            if emb is not None:
+                ops.colsum_cl(dl, N, rows2 // N, C, out_sample=emb[0][:, emb[1]:emb[1] + emb[2]])
+            if not need_dx:
+                return
+            dx = torch.empty((N * D * H * W, _ld(C)), dtype=torch.bfloat16, device=x.device)
+            ops.dwt3d_cl_bwd(dl, dh, dims4, C, dx, acc=self._partial(x), lll_scale=lll_scale, hi_scale=hi_scale,
+                             hi_sb=hi_sb)
+            self._set(x, dx)
+
+        self._tape.append(bwd)
+
+    def _idwt_t(self, lll, hi, dims4, C, y, emb=None, lll_scale=3.0):
+        N, D, H, W = dims4
+        ops.idwt3d_cl(lll, hi, dims4, C, y, bias=emb[3] if emb else None, lll_scale=lll_scale)
+        self._keep.append((lll, hi, y))
+        rows2 = N * (D // 2) * (H // 2) * (W // 2)
+
+        def bwd():
+            dy = self._take(y)
+            if dy is None:
+                return
+            if emb is not None:
+                ops.colsum_cl(dy, N, D * H * W, C, out_sample=emb[0][:, emb[1]:emb[1] + emb[2]])
+            dl = torch.empty((rows2, _ld(C)), dtype=torch.bfloat16, device=dy.device)
+            dh = self._partial(hi)
+            accumulate = dh is not None
+            if dh is None:
+                dh = torch.empty((7, rows2, _ld(C)), dtype=torch.bfloat16, device=dy.device)
+            ops.idwt3d_cl_bwd(dy, dims4, C, dl, dh, lll_acc=self._partial(lll), hi_accumulate=accumulate,
+                              lll_scale=lll_scale)
+            self._set(lll, dl)
+            self._set(hi, dh)
+
+        self._tape.append(bwd)
+
+    def _resblock_t(self, blk, x, skip, emb_all, d_emb_all, N, dims):
+        """ResBlock.forward (reference wunet.py:223-269) with the backward taped."""
+        dev = x.device
+        cin, cout = blk.channels, blk.out_channels
+        if blk.dropout:
+            raise NotImplementedError("dropout > 0 in training is not implemented (run.sh ships dropout=0)")
+        emb = self._emb_slice(blk, emb_all, d_emb_all)
+        gn1, conv1 = blk.in_layers[0], blk.in_layers[2]
+        skip_out = skip
+        d4 = (N,) + tuple(dims)
+        if blk.down:
+            h_full = self._gn_silu_conv(gn1, x, conv1, N, dims)
+            d2 = (dims[0] // 2, dims[1] // 2, dims[2] // 2)
+            s2 = d2[0] * d2[1] * d2[2]
+            h = self._buf(N * s2, cout, dev)
+            hi = torch.empty((7, N * s2, _ld(cout)), dtype=torch.bfloat16, device=dev)
+            self._dwt_t(h_full, d4, cout, h, hi, emb=emb, lll_scale=1.0 / 3.0)
+            xs = self._buf(N * s2, cin, dev)
+            self._dwt_t(x, d4, cin, xs, None, lll_scale=1.0 / 3.0)
+            x, dims, skip_out = xs, d2, hi
+        elif blk.up:
+            if skip is None:
+                raise FcwdmError("up-sampling ResBlock reached without stored high-frequency sub-bands")
+            h_low = self._gn_silu_conv(gn1, x, conv1, N, dims)
+            d2 = (dims[0] * 2, dims[1] * 2, dims[2] * 2)
+            s2 = d2[0] * d2[1] * d2[2]
+            h = self._buf(N * s2, cout, dev)
+            self._idwt_t(h_low, skip, (N,) + d2, cout, h, emb=emb, lll_scale=3.0)
+            xu = self._buf(N * s2, cin, dev)
+            self._idwt_t(x, skip, (N,) + d2, cin, xu, lll_scale=3.0)
+            x, dims, skip_out = xu, d2, None
+        else:
+            h = self._gn_silu_conv(gn1, x, conv1, N, dims, emb=emb, stats_groups=blk.out_layers[0].num_groups)
+        if isinstance(blk.skip_connection, torch.nn.Conv3d):
+            x = self._conv3d_t(blk.skip_connection, x, N, dims)
+        out = self._gn_silu_conv(blk.out_layers[0], h, blk.out_layers[3], N, dims, residual=x,
+                                 stats_groups=self.model.num_groups)
+        return out, skip_out, dims
+
+    # ------------------------------------------------------------------ whole network
+    def forward_train(self, x, timesteps):
+        """Planar fp32 (N, C, D, H, W) -> (N, out_channels, D, H, W), recording the backward tape."""
+        from guided_diffusion.wunet import ResBlock, WaveletDownsample
+        m = self.model
+        if not x.is_cuda:
+            raise FcwdmError("WavUNetModel.forward: input is on the CPU; the fcwdm denoiser has no CPU path")
+        if x.dim() != 5 or x.shape[1] != m.in_channels:
+            raise ValueError(f"expected input of shape (N, {m.in_channels}, D, H, W), got {tuple(x.shape)}")
+        if timesteps.is_floating_point():
+            raise NotImplementedError("fractional timesteps (rescale_timesteps=True) are not implemented")
+        N, C, D, H, W = x.shape
+        dims = (D, H, W)
+        levels = len(m.channel_mult)
+        for dim in dims:
+            if dim % (2 ** levels):
+                raise FcwdmError(f"spatial size {dims} is not divisible by 2^{levels}")
+        dev = x.device
+        with torch.cuda.device(dev):
+            self.prepare_train(dev)
+            self.flat_grad(dev)
+            self._tape, self._grads, self._keep = [], {}, []
+            self._stats.clear()
+            self._arena = torch.zeros(1 << 18, dtype=torch.float64, device=dev)
+            self._arena_pos = 0
+            S = D * H * W
+            x_cl = torch.zeros((N * S, _ld(C)), dtype=torch.bfloat16, device=dev)
+            ops.planar_to_cl(x.detach().float(), x_cl, C)
+            t = timesteps.to(torch.int64).contiguous()
+
+            # ---- timestep path (wunet.py:472-475,736; ResBlock emb_layers :203-206), pre-activations kept
+            l0, l2 = m.time_embed[0], m.time_embed[2]
+            te = torch.empty((N, m.model_channels), dtype=torch.float32, device=dev)
+            ops.timestep_embedding(t, te, m.model_channels)
+            z1 = torch.empty((N, l0.out_features), dtype=torch.float32, device=dev)
+            ops.linear(te, self._p32(l0.weight), self._p32(l0.bias), z1, act_in=0, act_out=0)
+            e2 = torch.empty((N, l2.out_features), dtype=torch.float32, device=dev)
+            ops.linear(z1, self._p32(l2.weight), self._p32(l2.bias), e2, act_in=1, act_out=0)
+            emb_all = self._emb_all(e2)
+            d_emb_all = torch.zeros_like(emb_all)
+
+            def emb_bwd():
+                seen = set()
+                for mod in m.modules():
+                    if isinstance(mod, ResBlock) and id(mod) not in seen:
+                        seen.add(id(mod))
+                        lin = mod.emb_layers[1]
+                        off, n = self._emb_off[id(mod)]
+                        ops.linear_bwd(e2, None, d_emb_all[:, off:off + n], dW=self._gp(lin.weight), db=self._gp(lin.bias),
+                                       act_in=1)
+                        self._param_done(lin.weight, lin.bias)
+                d_e2 = torch.empty_like(e2)
+                ops.linear_bwd(e2, self._emb_w, d_emb_all, dx=d_e2, act_in=1)
+                d_z1 = torch.empty_like(z1)
+                ops.linear_bwd(z1, self._p32(l2.weight), d_e2, dx=d_z1, dW=self._gp(l2.weight), db=self._gp(l2.bias), act_in=1)
+                ops.linear_bwd(te, None, d_z1, dW=self._gp(l0.weight), db=self._gp(l0.bias), act_in=0)
+                self._param_done(l2.weight, l2.bias, l0.weight, l0.bias)
+
+            self._tape.append(emb_bwd)
+
+            # ---- U-Net (mirrors WavUNetEngine.forward_cl / reference wunet.py:734-795)
+            hs = []
+            pyramid, pyr_dims, pyr_c = x_cl, dims, m.in_channels
+            h, hdims = x_cl, dims
+            first_pyramid = True
+            for module in m.input_blocks:
+                first = module[0]
+                if isinstance(first, WaveletDownsample):
+                    d2 = (pyr_dims[0] // 2, pyr_dims[1] // 2, pyr_dims[2] // 2)
+                    s2 = d2[0] * d2[1] * d2[2]
+                    cat = self._buf(N * s2, 8 * pyr_c, dev)
+                    self._dwt_t(pyramid, (N,) + pyr_dims, pyr_c, cat[:, :pyr_c], cat[:, pyr_c:], lll_scale=1.0 / 3.0,
+                                hi_scale=1.0 / 3.0, hi_sb=pyr_c, need_dx=not first_pyramid)
+                    first_pyramid = False
+                    pyramid = self._conv3d_t(first.conv, cat, N, d2, residual=h, stats_groups=m.num_groups)
+                    pyr_dims, pyr_c = d2, first.out_ch
+                    h = pyramid
+                    continue
+                skip = None
+                if isinstance(first, torch.nn.Conv3d):
+                    h = self._conv3d_t(first, h, N, hdims, stats_groups=m.num_groups, need_dx=False)
+                else:
+                    for layer in module:
+                        if not isinstance(layer, ResBlock):
+                            raise NotImplementedError(f"unsupported layer in input_blocks: {type(layer).__name__}")
+                        h, skip, hdims = self._resblock_t(layer, h, None, emb_all, d_emb_all, N, hdims)
+                hs.append(skip)
+            for layer in m.middle_block:
+                h, _, hdims = self._resblock_t(layer, h, None, emb_all, d_emb_all, N, hdims)
+            skip = None
+            for module in m.output_blocks:
+                new_hs = hs.pop()
+                if new_hs is not None:
+                    skip = new_hs
+                cur = skip
+                for layer in module:
+                    h, cur, hdims = self._resblock_t(layer, h, cur, emb_all, d_emb_all, N, hdims)
+            for module in m.out_res:
+                for layer in module:
+                    h, _, hdims = self._resblock_t(layer, h, None, emb_all, d_emb_all, N, hdims)
+            out_cl = self._gn_silu_conv(m.out[0], h, m.out[2], N, hdims, out_ld=max(8, (m.out_channels + 7) // 8 * 8))
+            self._out_cl = out_cl
+            self._shape = (N, D, H, W)
+            out = torch.empty((N, m.out_channels, D, H, W), dtype=torch.float32, device=dev)
+            ops.cl_to_planar(out_cl, out, m.out_channels)
+        return out.to(x.dtype) if x.dtype != torch.float32 else out
+
+    def backward(self, dout):
+        """dout: planar (N, out_channels, D, H, W).  Runs the tape in reverse; returns the flat fp32 gradient (views
+        per parameter through .grad_views())."""
+        m = self.model
+        N, D, H, W = self._shape
+        dev = dout.device
+        with torch.cuda.device(dev):
+            self._gflat.zero_()
+            if self.grad_ready_hook is not None:
+                self._uses_left = dict(self._use_count())
+            dy = torch.zeros((N * D * H * W, _ld(m.out_channels)), dtype=torch.bfloat16, device=dev)
+            ops.planar_to_cl(dout.detach().float().contiguous(), dy, m.out_channels)
+            self._set(self._out_cl, dy)
+            for fn in reversed(self._tape):
+                fn()
+            self._tape, self._grads, self._keep, self._out_cl = [], {}, [], None
+            self._stats.clear()
+        return self._gflat
+
+    def _use_count(self):
+        """How many tape entries contribute to each parameter (weight-tied blocks run twice)."""
+        from guided_diffusion.wunet import ResBlock
+        cnt = {id(p): 0 for p in self.model.parameters()}
+        m = self.model
+
+        def visit_block(blk):
+            for p in blk.parameters():
+                cnt[id(p)] += 1
+
+        for module in m.input_blocks:
+            for layer in module:
+                visit_block(layer)
+        for layer in m.middle_block:
+            visit_block(layer)
+        for module in m.output_blocks:
+            for layer in module:
+                visit_block(layer)
+        for module in m.out_res:
+            for layer in module:
+                visit_block(layer)
+        for p in m.out.parameters():
+            cnt[id(p)] += 1
+        for p in m.time_embed.parameters():
+            cnt[id(p)] += 1
+        return cnt
+
+    def grad_views(self):
+        return [self._gview[id(p)] for p in self.model.parameters()]
+
+
+class WavUNetFunction(torch.autograd.Function):
+    """Autograd boundary: one node for the whole denoiser.  Inputs: the engine, x, timesteps, then every parameter
+    (so autograd routes their gradients to .grad / DDP hooks).  The gradient w.r.t. x is not computed (the training
+    loss, gaussian_diffusion.py:1084-1166, never needs it)."""
+
+    @staticmethod
+    def forward(ctx, engine, x, timesteps, *params):
+        ctx.engine = engine
+        ctx.n_params = len(params)
+        return engine.forward_train(x, timesteps)
+
+    @staticmethod
+    def backward(ctx, dout):
+        eng = ctx.engine
+        eng.backward(dout)
+        return (None, None, None) + tuple(eng.grad_views())

@@ -192,6 +192,59 @@ int fcwdm_conv3d_pair_fwd(const void* x, int64_t x_ld, const void* wp, const flo
                           const float* gn_in_beta, int64_t gn_in_groups, float gn_in_eps, int64_t N, int64_t D,
                           int64_t H, int64_t W, int64_t Cin, int64_t Cout, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Training path (scripts/train.py -> TrainLoop.forward_backward, guided_diffusion/train_util.py:396-460): the
+ * reference differentiates WavUNetModel with autograd (cuDNN dgrad/wgrad, native GroupNorm/SiLU backward, the
+ * matmul DWT/IDWT backward of DWT_IDWT_Functions.py:139-156,184-208).  Here the backward is the explicit kernels
+ * below on channels-last bf16 gradients; parameter gradients are fp32 in the reference's layouts and ACCUMULATE
+ * into their destinations (zeroed once per step by the caller), which weight-tied ResBlocks (wunet.py:647-673) need.
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* K5w: conv3d weight gradient, dW[co][ci][kd][kh][kw] (=, or += when accumulate) sum_v dY[v][co] * X[v + off][ci],
+ * a tcgen05 GEMM with both operands MN-major (csrc/conv3d_wgrad.cu).  x: the conv's INPUT, cl bf16 with x_ld >=
+ * round_up(Cin, 64) readable finite channels; dy: gradient of the conv's output, cl bf16 with dy_ld >= round_up(Cout, 64).
+ * workspace: device scratch of fcwdm_conv3d_wgrad_workspace_bytes(...) bytes (per-split fp32 partial sums). */
+int64_t fcwdm_conv3d_wgrad_workspace_bytes(int64_t N, int64_t D, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                                           int ksize);
+int fcwdm_conv3d_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw, void* workspace,
+                       int64_t workspace_bytes, int accumulate, int64_t N, int64_t D, int64_t H, int64_t W, int64_t Cin,
+                       int64_t Cout, int ksize, void* stream);
+/* conv3d data gradient = fcwdm_conv3d_fwd / fcwdm_conv3d_pair_fwd of dY with these weights:
+ * wt[ci][co][tap] = w[co][ci][taps-1-tap] (f32, standard layout; pack it with the forward packers). */
+int fcwdm_conv3d_transpose_flip_weights(const float* w, float* wt, int64_t Cout, int64_t Cin, int ksize, void* stream);
+
+/* GroupNorm(+SiLU) backward (nn.py:17-19): given x, the forward statistics (fcwdm_groupnorm_stats layout) and
+ * dy = dL/d SiLU(GN(x)), writes dx (+ acc[voxel*acc_ld + c] if acc != NULL: gradient fan-in of x) and ADDS into
+ * dgamma[C], dbeta[C] (either may be NULL).  sums: scratch double [N][FCWDM_GN_STAT_REPLICAS][C][2], zeroed here. */
+int fcwdm_groupnorm_bwd(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, const double* stats,
+                        const float* gamma, const float* beta, double* sums, const void* acc, int64_t acc_ld, void* dx,
+                        int64_t dx_ld, float* dgamma, float* dbeta, int64_t N, int64_t S, int64_t C, int64_t G, float eps,
+                        int silu, void* stream);
+/* column sums of a cl bf16 tensor (conv bias and timestep-embedding gradients): out_sample[n*os_ld + c] += sum_v,
+ * out_total[c] += sum_{n,v}; either may be NULL. */
+int fcwdm_colsum_cl(const void* x, int64_t ld, float* out_sample, int64_t os_ld, float* out_total, int64_t N, int64_t S,
+                    int64_t C, void* stream);
+/* adjoint of fcwdm_dwt3d_cl: dx = IDWT(lll_scale*dlll, hi_scale*dhi (zero when dhi == NULL)) (+ acc). (D,H,W) = dx dims. */
+int fcwdm_dwt3d_cl_bwd(const void* dlll, int64_t lll_ld, const void* dhi, int64_t hi_ld, int64_t hi_sb, const void* acc,
+                       int64_t acc_ld, void* dx, int64_t dx_ld, int64_t N, int64_t D, int64_t H, int64_t W, int64_t C,
+                       float lll_scale, float hi_scale, void* stream);
+/* adjoint of fcwdm_idwt3d_cl: dlll = lll_scale*LLL(dy) (+ lll_acc), dhi (=, += when hi_accumulate) the 7 high bands of
+ * dy; dlll or dhi may be NULL.  (D,H,W) = dy dims. */
+int fcwdm_idwt3d_cl_bwd(const void* dy, int64_t dy_ld, const void* lll_acc, int64_t acc_ld, void* dlll, int64_t lll_ld,
+                        void* dhi, int64_t hi_ld, int64_t hi_sb, int hi_accumulate, int64_t N, int64_t D, int64_t H,
+                        int64_t W, int64_t C, float lll_scale, void* stream);
+/* y = a + b on cl bf16 buffers (rows x C). */
+int fcwdm_add_cl(const void* a, int64_t a_ld, const void* b, int64_t b_ld, void* y, int64_t y_ld, int64_t rows, int64_t C,
+                 void* stream);
+/* backward of fcwdm_linear with act_out = 0: dW[m][k] += sum_n dy[n][m]*act(x[n][k]), db[m] += sum_n dy[n][m],
+ * dx[n][k] (=, += when accumulate_dx) act'(x[n][k]) * sum_m dy[n][m]*W[m][k]; dW/db/dx may be NULL. */
+int fcwdm_linear_bwd(const float* x, const float* W, const float* dy, int64_t dy_ld, float* dx, float* dW, float* db,
+                     int64_t N, int64_t K, int64_t M, int act_in, int accumulate_dx, void* stream);
+/* Fused AdamW step over a flat fp32 range (torch.optim.AdamW semantics; train_util.py:75-82,391); the gradient is
+ * multiplied by grad_scale first (1/world_size after a sum all-reduce). step counts from 1. */
+int fcwdm_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                float weight_decay, int64_t step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
