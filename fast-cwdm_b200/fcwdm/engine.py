@@ -91,6 +91,10 @@ class WavUNetEngine:
         self._sig = sig
         self._device = device
 
+    def invalidate(self):
+        """Forget the packed weights (the parameters were updated through raw pointers, e.g. fcwdm.optim.FusedAdamW)."""
+        self._sig = None
+
     def _p32(self, p):
         """fp32 contiguous view of a (GroupNorm / Linear) parameter."""
         t = self._f32.get(id(p))

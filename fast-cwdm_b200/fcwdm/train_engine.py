@@ -69,6 +69,10 @@ class WavUNetTrainEngine(WavUNetEngine):
                 self._conv_t[id(mod)] = pk
         self._tsig = self._sig
 
+    def invalidate(self):
+        super().invalidate()
+        self._tsig = None
+
     # ------------------------------------------------------------------ gradient bookkeeping
     def _take(self, t):
         return self._grads.pop(id(t), None)
@@ -85,9 +89,16 @@ class WavUNetTrainEngine(WavUNetEngine):
         if cur is None:
             self._grads[id(t)] = g
         else:
-            out = torch.empty((rows, _ld(C)), dtype=torch.bfloat16, device=g.device)
+            out = self._buf(rows, C, g.device)
             ops.add_cl(cur, g, out, rows, C)
             self._grads[id(t)] = out
+
+    @staticmethod
+    def _buf7(rows, c, device):
+        """The 7 high-frequency bands (7, rows, ld); pad channels (C < ld) must be zero: they meet zero weights in a conv."""
+        ld = _ld(c)
+        alloc = torch.empty if ld == c else torch.zeros
+        return alloc((7, rows, ld), dtype=torch.bfloat16, device=device)
 
     def _zeros_like_grad(self, rows, C, device):
         return torch.zeros((rows, _ld(C)), dtype=torch.bfloat16, device=device)
@@ -119,7 +130,7 @@ class WavUNetTrainEngine(WavUNetEngine):
             ops.conv3d_wgrad(x, dy, self._gp(mod.weight), dims4, pk.cin, pk.cout, pk.k, accumulate=True)
             if need_dx:
                 pt = self._conv_t[id(mod)]
-                dx = torch.empty((rows, _ld(pk.cin)), dtype=torch.bfloat16, device=dy.device)
+                dx = self._buf(rows, pk.cin, dy.device)
                 acc = self._partial(x)
                 if pt.pair:
                     ops.conv3d_pair_cl(dy, pt.wp, None, dx, dims4, pt.cin, pt.cout, residual=acc)
@@ -143,7 +154,7 @@ class WavUNetTrainEngine(WavUNetEngine):
             dy = self._take(y)
             if dy is None:
                 return
-            dx = torch.empty((N * S, _ld(C)), dtype=torch.bfloat16, device=x.device)
+            dx = self._buf(N * S, C, x.device)
             ops.groupnorm_bwd(x, dy, stats, gamma, beta, dx, self._gp(gn.weight), self._gp(gn.bias), N, S, C,
                               gn.num_groups, gn.eps, silu, acc=self._partial(x))
             self._set(x, dx)
@@ -168,18 +179,19 @@ class WavUNetTrainEngine(WavUNetEngine):
         off, n = self._emb_off[id(blk)]
         return (d_emb_all, off, n, emb_all[:, off:off + n])
 
-    def _dwt_t(self, x, dims4, C, lll, hi, emb=None, lll_scale=1.0 / 3.0, hi_scale=1.0, hi_sb=None, need_dx=True):
+    def _dwt_t(self, x, dims4, C, lll, hi, emb=None, lll_scale=1.0 / 3.0, hi_scale=1.0, hi_sb=None, need_dx=True,
+               cat=None):
         N, D, H, W = dims4
         ops.dwt3d_cl(x, dims4, C, lll, hi, lll_bias=emb[3] if emb else None, lll_scale=lll_scale, hi_scale=hi_scale,
                      hi_sb=hi_sb)
         self._keep.append((x, lll, hi))
         rows2 = N * (D // 2) * (H // 2) * (W // 2)
-        # the concatenated WaveletDownsample output is ONE tensor (lll and hi are views of it): key on its base
-        key_l = lll._base if (hi_sb is not None and lll._base is not None) else lll
+        # WaveletDownsample: lll and hi are column slices of ONE tensor `cat` (the conv's operand): its gradient is keyed
+        # on `cat`
 
         def bwd():
-            if hi_sb is not None:
-                dcat = self._take(key_l)
+            if cat is not None:
+                dcat = self._take(cat)
                 if dcat is None:
                     return
                 dl, dh = dcat[:, :C], dcat[:, C:]
@@ -194,7 +206,7 @@ class WavUNetTrainEngine(WavUNetEngine):
                 ops.colsum_cl(dl, N, rows2 // N, C, out_sample=emb[0][:, emb[1]:emb[1] + emb[2]])
             if not need_dx:
                 return
-            dx = torch.empty((N * D * H * W, _ld(C)), dtype=torch.bfloat16, device=x.device)
+            dx = self._buf(N * D * H * W, C, x.device)
             ops.dwt3d_cl_bwd(dl, dh, dims4, C, dx, acc=self._partial(x), lll_scale=lll_scale, hi_scale=hi_scale,
                              hi_sb=hi_sb)
             self._set(x, dx)
@@ -213,11 +225,11 @@ class WavUNetTrainEngine(WavUNetEngine):
                 return
             if emb is not None:
                 ops.colsum_cl(dy, N, D * H * W, C, out_sample=emb[0][:, emb[1]:emb[1] + emb[2]])
-            dl = torch.empty((rows2, _ld(C)), dtype=torch.bfloat16, device=dy.device)
+            dl = self._buf(rows2, C, dy.device)
             dh = self._partial(hi)
             accumulate = dh is not None
             if dh is None:
-                dh = torch.empty((7, rows2, _ld(C)), dtype=torch.bfloat16, device=dy.device)
+                dh = self._buf7(rows2, C, dy.device)
             ops.idwt3d_cl_bwd(dy, dims4, C, dl, dh, lll_acc=self._partial(lll), hi_accumulate=accumulate,
                               lll_scale=lll_scale)
             self._set(lll, dl)
@@ -240,7 +252,7 @@ class WavUNetTrainEngine(WavUNetEngine):
             d2 = (dims[0] // 2, dims[1] // 2, dims[2] // 2)
             s2 = d2[0] * d2[1] * d2[2]
             h = self._buf(N * s2, cout, dev)
-            hi = torch.empty((7, N * s2, _ld(cout)), dtype=torch.bfloat16, device=dev)
+            hi = self._buf7(N * s2, cout, dev)
             self._dwt_t(h_full, d4, cout, h, hi, emb=emb, lll_scale=1.0 / 3.0)
             xs = self._buf(N * s2, cin, dev)
             self._dwt_t(x, d4, cin, xs, None, lll_scale=1.0 / 3.0)
@@ -336,9 +348,10 @@ class WavUNetTrainEngine(WavUNetEngine):
                     s2 = d2[0] * d2[1] * d2[2]
                     cat = self._buf(N * s2, 8 * pyr_c, dev)
                     self._dwt_t(pyramid, (N,) + pyr_dims, pyr_c, cat[:, :pyr_c], cat[:, pyr_c:], lll_scale=1.0 / 3.0,
-                                hi_scale=1.0 / 3.0, hi_sb=pyr_c, need_dx=not first_pyramid)
+                                hi_scale=1.0 / 3.0, hi_sb=pyr_c, need_dx=not first_pyramid, cat=cat)
+                    pyramid = self._conv3d_t(first.conv, cat, N, d2, residual=h, stats_groups=m.num_groups,
+                                             need_dx=not first_pyramid)     # level 0: cat derives from the input only
                     first_pyramid = False
-                    pyramid = self._conv3d_t(first.conv, cat, N, d2, residual=h, stats_groups=m.num_groups)
                     pyr_dims, pyr_c = d2, first.out_ch
                     h = pyramid
                     continue
@@ -418,7 +431,15 @@ class WavUNetTrainEngine(WavUNetEngine):
         return cnt
 
     def grad_views(self):
-        return [self._gview[id(p)] for p in self.model.parameters()]
+        """Per-parameter views of a COPY of the flat gradient (autograd may adopt them as .grad and later accumulate
+        into them in place; the engine's own buffer is rewritten by the next backward).  The copy is one contiguous
+        buffer (self.last_flat) so fcwdm.optim.FusedAdamW can step on it with one launch."""
+        self.last_flat = self._gflat.clone()
+        return [self.last_flat[lo:hi].view(p.shape) for p in self.model.parameters()
+                for lo, hi in (self._goff[id(p)],)]
+
+    def flat_offsets(self):
+        return [self._goff[id(p)] for p in self.model.parameters()]
 
 
 class WavUNetFunction(torch.autograd.Function):

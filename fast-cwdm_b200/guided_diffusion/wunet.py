@@ -245,6 +245,7 @@ class WavUNetModel(nn.Module):
         self.out = nn.Sequential(normalization(ch, num_groups), nn.SiLU(),
                                  conv_nd(dims, model_channels, out_channels, 3, padding=1))
         self._engine = None
+        self._train_engine = None
 
     # the reference overrides .to() to support a (broken for WavUNet) 2-device split and to return None
     # (wunet.py:707-732).  Here: a 1-element list/tuple is unwrapped, >1 devices is refused, and the module is
@@ -266,12 +267,28 @@ class WavUNetModel(nn.Module):
             object.__setattr__(self, "_engine", WavUNetEngine(self))
         return self._engine
 
+    def train_engine(self):
+        if getattr(self, "_train_engine", None) is None:
+            from fcwdm.train_engine import WavUNetTrainEngine
+            object.__setattr__(self, "_train_engine", WavUNetTrainEngine(self))
+        return self._train_engine
+
     def forward(self, x, timesteps):
-        """x: [N, C, D, H, W] fp32, timesteps: [N] -> [N, out_channels, D, H, W].  Inference only this round:
-        the conv/GroupNorm backward kernels are not written yet, so a call that would need autograd raises."""
-        if th.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(
-                "WavUNetModel.forward under autograd: the fcwdm backward kernels (conv dgrad/wgrad, GroupNorm) are "
-                "not implemented yet; wrap inference in torch.no_grad() (p_sample_loop does)")
+        """x: [N, C, D, H, W] fp32, timesteps: [N] -> [N, out_channels, D, H, W].
+
+        Under ``torch.no_grad()`` (sampling) this is the fused inference plan.  With autograd enabled and trainable
+        parameters (scripts/train.py) the forward records a tape and the returned tensor carries ONE autograd node whose
+        backward runs the explicit fcwdm backward kernels (fcwdm/train_engine.py) and hands every parameter its fp32
+        gradient; the gradient w.r.t. ``x`` is not produced (training_losses never asks for it)."""
         self.hs_shapes = []
+        if th.is_grad_enabled():
+            params = [p for p in self.parameters()]
+            if any(p.requires_grad for p in params):
+                if not all(p.requires_grad for p in params):
+                    raise NotImplementedError("partially frozen WavUNetModel: the fcwdm backward produces gradients for "
+                                              "all parameters or none")
+                from fcwdm.train_engine import WavUNetFunction
+                return WavUNetFunction.apply(self.train_engine(), x, timesteps, *params)
+            if x.requires_grad:
+                raise NotImplementedError("gradient w.r.t. the denoiser input is not implemented by the fcwdm backward")
         return self.engine().forward(x, timesteps)

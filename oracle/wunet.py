@@ -15,12 +15,48 @@ import torch.nn.functional as F
 from . import haar
 
 
+_S = 0.7071067811865476   # cast to fp32 by the tensor arithmetic below, as torch.Tensor(matrix) does (layer.py:506-518)
+
+
+def _analysis(x, dim):
+    """Same operations, in the same order, as oracle.haar._analysis, but in torch so that autograd differentiates
+    through the wavelet up/down-sampling (the reference's backward is DWT_IDWT_Functions.py:139-156)."""
+    idx0 = [slice(None)] * x.dim()
+    idx1 = [slice(None)] * x.dim()
+    idx0[dim], idx1[dim] = slice(0, None, 2), slice(1, None, 2)
+    a, b = x[tuple(idx0)], x[tuple(idx1)]
+    return _S * a + _S * b, _S * a - _S * b
+
+
+def _synthesis(lo, hi, dim):
+    even, odd = _S * lo + _S * hi, _S * lo - _S * hi
+    out = torch.stack([even, odd], dim=dim + 1)
+    shape = list(lo.shape)
+    shape[dim] *= 2
+    return out.reshape(shape)
+
+
 def _dwt(x):
-    return tuple(torch.from_numpy(b.copy()) for b in haar.dwt3d(x.detach().numpy()))
+    """oracle.haar.dwt3d in torch (H, then W, then D; DWT_IDWT_Functions.py:122-135)."""
+    L, H = _analysis(x, 3)
+    LL, LH = _analysis(L, 4)
+    HL, HH = _analysis(H, 4)
+    LLL, HLL = _analysis(LL, 2)
+    LLH, HLH = _analysis(LH, 2)
+    LHL, HHL = _analysis(HL, 2)
+    LHH, HHH = _analysis(HH, 2)
+    return LLL, LLH, LHL, LHH, HLL, HLH, HHL, HHH
 
 
-def _idwt(*bands):
-    return torch.from_numpy(haar.idwt3d(*[b.detach().numpy() for b in bands]).copy())
+def _idwt(LLL, LLH, LHL, LHH, HLL, HLH, HHL, HHH):
+    """oracle.haar.idwt3d in torch (D, then W, then H; DWT_IDWT_Functions.py:167-180)."""
+    LL = _synthesis(LLL, HLL, 2)
+    LH = _synthesis(LLH, HLH, 2)
+    HL = _synthesis(LHL, HHL, 2)
+    HH = _synthesis(LHH, HHH, 2)
+    L = _synthesis(LL, LH, 4)
+    H = _synthesis(HL, HH, 4)
+    return _synthesis(L, H, 3)
 
 
 def timestep_embedding(timesteps, dim, max_period=10000):
@@ -66,7 +102,7 @@ def _resblock(sd, p, x, skip, emb, groups, up=False, down=False):
 
 def wunet_forward(sd, x, timesteps, *, model_channels, channel_mult, num_res_blocks=2, num_groups=32):
     """WavUNetModel.forward (:734-795) for the module list built by __init__ (:480-705)."""
-    sd = {k: v.detach().float() for k, v in sd.items()}
+    sd = {k: (v if v.dtype == torch.float32 else v.float()) for k, v in sd.items()}   # keeps autograd leaves (oracle.train)
     L = len(channel_mult)
     emb = timestep_embedding(timesteps, model_channels)                                    # :745
     emb = F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])

@@ -60,7 +60,7 @@ def test_no_cpu_fallback():
     model, diffusion = create_model_and_diffusion(**args)
     with torch.no_grad(), pytest.raises(FcwdmError):
         model(torch.zeros(1, 32, 4, 4, 4), torch.zeros(1, dtype=torch.long))
-    with pytest.raises(NotImplementedError):          # autograd path not implemented this round: fail loudly
+    with pytest.raises(FcwdmError):                   # training (autograd) path: CUDA only as well, no CPU fallback
         model(torch.zeros(1, 32, 4, 4, 4), torch.zeros(1, dtype=torch.long))
 
 

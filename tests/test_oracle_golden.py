@@ -133,3 +133,38 @@ def test_loop_small(golden):
     for k, i in enumerate(reversed(range(tab.num_timesteps))):
         img = od.p_sample(tab, model, img, torch.tensor([i]), cond=cond, timestep_map=list(g["tmap"]))["sample"]
         np.testing.assert_allclose(img.numpy(), g["samples"][k], atol=2e-4)
+
+
+def test_training_step_small(golden):
+    """Loss, every parameter gradient and the AdamW update of one reference training step (train_small.npz)."""
+    from oracle import train as otr
+    g = golden("train_small")
+    sd = _small_sd(golden)
+    tab, m10 = _tab10()
+    batch = {k: torch.from_numpy(g["batch_" + k]) for k in ("t1n", "t1c", "t2w", "t2f")}
+    loss, mse, out, grads = otr.training_step_grads(sd, tab, batch, torch.from_numpy(g["t"]), torch.from_numpy(g["noise"]),
+                                                    model_channels=32, channel_mult=(1, 2), timestep_map=m10)
+    np.testing.assert_allclose(mse.numpy(), g["mse_wav"], rtol=2e-5)
+    assert abs(float(loss) - float(g["loss"])) <= 2e-5 * float(g["loss"])
+    np.testing.assert_allclose(out.numpy(), g["model_output"], atol=5e-5 * float(np.abs(g["model_output"]).max()))
+    names = [str(n) for n in g["param_names"]]
+    assert len(names) == 178
+    for name, ref_norm in zip(names, g["grad_norms"]):
+        gr = grads[name]
+        assert abs(float(gr.double().norm()) - ref_norm) <= 1e-3 * ref_norm + 1e-6, name   # exact-zero gradients (a per-channel
+        # constant in front of a 1-channel-per-group GroupNorm) are rounding noise ~1e-9 on both sides
+        if "grad/" + name in g.files:
+            ref = g["grad/" + name]
+            np.testing.assert_allclose(gr.numpy(), ref, atol=1e-3 * float(np.abs(ref).max()) + 1e-7, err_msg=name)
+        else:
+            ref = g["gradslice/" + name]
+            np.testing.assert_allclose(gr[:2].numpy(), ref, atol=1e-3 * float(np.abs(ref).max()) + 1e-7, err_msg=name)
+    for key in g.files:
+        if key.startswith("stepped/"):
+            name = key[len("stepped/"):]
+            p, _, _ = otr.adamw_step(sd[name], grads[name], torch.zeros_like(sd[name]), torch.zeros_like(sd[name]), 1,
+                                     float(g["lr"]), weight_decay=float(g["wd"]))
+            # Adam's first step moves every weight by ~lr * sign(g): where the true gradient is exactly zero the sign is
+            # rounding noise, so compare only where |g| is far above eps = 1e-8
+            mask = np.abs(g["grad/" + name]) > 1e-5
+            np.testing.assert_allclose(p.numpy()[mask], g[key][mask], atol=2e-5, err_msg=name)
