@@ -393,6 +393,143 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------
+# training arm (BASELINE config 4): one "step" = training_losses forward + fcwdm backward + fused AdamW on a batch of
+# B synthetic cases per GPU; data-parallel over N GPUs with ONE bucketed NCCL gradient all-reduce per step
+# ----------------------------------------------------------------------------------------------------
+def time_wgrad_kernel(device, iters=10):
+    """conv3d wgrad 64->64 3x3x3 @112x112x80 alone (the dominant training kernel), CUDA events, L2 flush between."""
+    from fcwdm import ops
+    S = LATENT[0] * LATENT[1] * LATENT[2]
+    x = torch.randn((S, 64), device=device).to(torch.bfloat16)
+    dy = torch.randn((S, 64), device=device).to(torch.bfloat16)
+    dw = torch.zeros((64, 64, 3, 3, 3), device=device)
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=device)
+    for _ in range(3):
+        ops.conv3d_wgrad(x, dy, dw, (1,) + LATENT, 64, 64, 3, accumulate=False)
+    total = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.conv3d_wgrad(x, dy, dw, (1,) + LATENT, 64, 64, 3, accumulate=False)
+        e1.record()
+        e1.synchronize()
+        total += e0.elapsed_time(e1)
+    return total / iters, 2.0 * S * 64 * 64 * 27
+
+
+def run_train(args):
+    import torch.distributed as dist
+    from fcwdm import ddp, native
+    from fcwdm.optim import FusedAdamW
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the fcwdm training path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    peaks = measured_peaks()
+    model, diffusion = build_model(device)
+    model.train()
+    sync = None
+    if world > 1:
+        ddp.broadcast_parameters(model)
+        sync = ddp.attach(model)
+    opt = FusedAdamW(model, lr=1e-5, weight_decay=0.0)                      # run.sh:60 lr, train_util.py:75-82
+    B = args.batch
+    g = torch.Generator().manual_seed(100 + rank)                            # per-rank data (SURVEY 8e: seed + rank)
+    host = {k: torch.rand((B, 1) + IMAGE, generator=g).pin_memory() for k in ("t1n", "t1c", "t2w", "t2f")}
+    dev_batch = {k: v.to(device) for k, v in host.items()}
+    slot = {k: torch.empty_like(v) for k, v in dev_batch.items()}
+    ones = torch.ones(8, device=device)
+    rng = torch.Generator(device=device).manual_seed(7 + rank)
+    last = {}
+
+    def step(batch):
+        opt.zero_grad()
+        t = torch.randint(0, diffusion.num_timesteps, (B,), device=device, generator=rng)
+        terms, _, _ = diffusion.training_losses(model, batch, t, model_kwargs={}, mode="i2i", contr="t1n")
+        loss = (terms["mse_wav"] * ones).mean()                              # train_util.py:447-449
+        loss.backward()
+        opt.step()
+        last["loss"] = loss.detach()
+
+    def step_resident():
+        step(dev_batch)
+
+    def step_e2e():
+        for k in slot:
+            slot[k].copy_(host[k], non_blocking=True)                        # H2D of this step's batch (pinned)
+        step(slot)
+        last["host_loss"] = float(last["loss"])                              # D2H read of the step's result
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def timed(fn, k, w):
+        for _ in range(w):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    warm = max(args.warmup, 3)
+    timed(step_resident, 0, warm)
+    clocks = ClockSampler(local)
+    clocks.start()
+    n0 = native.launch_count
+    ms_res = timed(step_resident, args.steps, 0)
+    launches = native.launch_count - n0
+    clk = clocks.stop()
+    ms_e2e = timed(step_e2e, args.steps, 1)
+    finite = bool(torch.isfinite(last["loss"]))
+    if rank == 0:
+        samples = args.steps * world * B
+        h2d = sum(v.numel() * 4 for v in host.values())
+        flop_step = 3.0 * CONV_FLOP_PER_STEP * B                             # fwd + dgrad + wgrad
+        result = {
+            "metric": "WavUNetModel training samples/sec", "value": samples / (ms_res * 1e-3), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_res / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"training step (training_losses i2i + backward + AdamW), WavUNetModel CFG-W4, "
+                                   f"batch {B} x 224x224x160 per GPU, bf16 compute / fp32 master",
+                       "parallelism": f"dp{world}: one bucketed NCCL gradient all-reduce (mean) per step" if world > 1
+                       else "single GPU", "l2": "per-step activations ~6 GB >> 126 MB L2 (no flush needed)",
+                       "allreduce_buckets": sync.launched if sync else 0, "peaks": peaks["src"], "loss_finite": finite,
+                       "final_loss": float(last["loss"])},
+            "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clk,
+            "step_tflops": flop_step * args.steps * world / (ms_res * 1e-3) / 1e12,
+        }
+        ms_k, flop = time_wgrad_kernel(device)
+        ach = flop / (ms_k * 1e-3) / 1e12
+        result["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                              "frac": ach / peaks["tf_burst"], "traffic": None,
+                              "kernel": "conv3d_wgrad_kernel<64,64,3,3> + finalize, 64->64 @112x112x80",
+                              "us_per_launch": ms_k * 1e3, "flop_per_launch": flop}
+        result["cpu_baseline"] = None
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -401,9 +538,13 @@ def main():
     ap.add_argument("--impl", default="fcwdm", choices=["fcwdm", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=1, help="volumes per GPU per step (BASELINE config 3 uses 8)")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
+                    help="sample = BASELINE config 2/3 (the headline, default); train = config 4 training step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_gpu(args)
 

@@ -33,6 +33,7 @@ class WavUNetTrainEngine(WavUNetEngine):
         self._grads = {}
         self._keep = []
         self.grad_ready_hook = None      # callable(lo, hi): flat-gradient range [lo, hi) is final (fcwdm.ddp)
+        self.grad_sync = None            # fcwdm.ddp.GradSync: bucketed all-reduce overlapped with the backward
 
     # ------------------------------------------------------------------ parameters / gradients
     def flat_grad(self, device):
@@ -394,11 +395,15 @@ class WavUNetTrainEngine(WavUNetEngine):
             self._gflat.zero_()
             if self.grad_ready_hook is not None:
                 self._uses_left = dict(self._use_count())
+            if self.grad_sync is not None:
+                self.grad_sync.begin()
             dy = torch.zeros((N * D * H * W, _ld(m.out_channels)), dtype=torch.bfloat16, device=dev)
             ops.planar_to_cl(dout.detach().float().contiguous(), dy, m.out_channels)
             self._set(self._out_cl, dy)
             for fn in reversed(self._tape):
                 fn()
+            if self.grad_sync is not None:
+                self.grad_sync.finish()
             self._tape, self._grads, self._keep, self._out_cl = [], {}, [], None
             self._stats.clear()
         return self._gflat
