@@ -224,32 +224,37 @@ __global__ void __launch_bounds__(256, 1) conv3d_wgrad_kernel(const __grid_const
     }
 }
 
-// dW[co][ci][tap] (+)= sum over splits of ws[split][tap][co][ci].  One block = one output channel x 32 input
-// channels: coalesced reads along ci, shared-memory transpose, coalesced writes of the 32 x taps contiguous floats.
+// dW[co][ci][tap] (+)= sum over splits of ws[split][tap][co][ci].  One block = one (tap, output channel, 32 input
+// channels): 8 thread groups stride over the splits with coalesced 128-byte reads, a shared-memory tree adds the 8
+// partial sums in a fixed order (deterministic), 32 threads scatter the result into the reference's layout.
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ dw,
                                                              int n_split, int taps, int Cout, int Cin, int co_p,
                                                              int ci_p, int accumulate) {
     pdl_prologue();
-    __shared__ float tile[27][33];
+    __shared__ float part[8][32];
+    const int tap = blockIdx.z;
     const int co = blockIdx.y;
-    const int cib = blockIdx.x * 32;
+    const int c = threadIdx.x & 31, lane = threadIdx.x >> 5;
+    const int ci = blockIdx.x * 32 + c;
     const size_t split_stride = (size_t)taps * co_p * ci_p;
-    for (int i = threadIdx.x; i < taps * 32; i += blockDim.x) {
-        const int tap = i >> 5, c = i & 31;
-        float a = 0.f;
-        if (cib + c < Cin) {
-            const float* p = ws + ((size_t)tap * co_p + co) * ci_p + cib + c;
-            for (int s = 0; s < n_split; ++s) a += p[s * split_stride];
+    float a = 0.f;
+    if (ci < Cin) {
+        const float* p = ws + ((size_t)tap * co_p + co) * ci_p + ci;
+        float a0 = 0.f, a1 = 0.f;
+        int s = lane;
+        for (; s + 8 < n_split; s += 16) {
+            a0 += p[(size_t)s * split_stride];
+            a1 += p[(size_t)(s + 8) * split_stride];
         }
-        tile[tap][c] = a;
+        if (s < n_split) a0 += p[(size_t)s * split_stride];
+        a = a0 + a1;
     }
+    part[lane][c] = a;
     __syncthreads();
-    const int n_ci = (Cin - cib) < 32 ? (Cin - cib) : 32;
-    float* out = dw + ((size_t)co * Cin + cib) * taps;
-    for (int i = threadIdx.x; i < n_ci * taps; i += blockDim.x) {
-        const int c = i / taps, tap = i % taps;
-        const float v = tile[tap][c];
-        out[i] = accumulate ? out[i] + v : v;
+    if (lane == 0 && ci < Cin) {
+        float v = ((part[0][c] + part[1][c]) + (part[2][c] + part[3][c])) + ((part[4][c] + part[5][c]) + (part[6][c] + part[7][c]));
+        float* out = dw + ((size_t)co * Cin + ci) * taps + tap;
+        *out = accumulate ? *out + v : v;
     }
 }
 
@@ -334,7 +339,7 @@ static WgPlan wg_plan(int64_t N, int64_t D, int64_t H, int64_t W, int64_t Cin, i
     p.n_nb = p.ci_p / p.n_tile;
     p.num_tiles = N * D * ((H + 15) / 16) * ((W + 7) / 8);
     const long long per_split = (long long)p.groups * p.n_mb * p.n_nb;
-    long long s = (2ll * num_sms() + per_split - 1) / per_split;     // about two waves of CTAs
+    long long s = num_sms() / per_split;                             // one full wave of CTAs (one CTA per SM)
     if (s > p.num_tiles) s = p.num_tiles;
     if (s > 1024) s = 1024;
     if (s < 1) s = 1;
@@ -441,7 +446,7 @@ extern "C" int fcwdm_conv3d_wgrad(const void* x, int64_t x_ld, const void* dy, i
     }
     FCWDM_REQUIRE(rc != FCWDM_ERR_UNSUPPORTED, FCWDM_ERR_UNSUPPORTED, "fcwdm_conv3d_wgrad: no kernel variant for this shape");
     if (rc) return rc;
-    launch_k(wgrad_finalize_kernel, dim3((unsigned)((Cin + 31) / 32), (unsigned)Cout), dim3(256), 0, st,
+    launch_k(wgrad_finalize_kernel, dim3((unsigned)((Cin + 31) / 32), (unsigned)Cout, (unsigned)taps), dim3(256), 0, st,
              (const float*)workspace, dw, p.n_split, taps, (int)Cout, (int)Cin, p.co_p, p.ci_p, accumulate);
     FCWDM_CHECK_LAUNCH("fcwdm_conv3d_wgrad (finalize)");
     return FCWDM_OK;

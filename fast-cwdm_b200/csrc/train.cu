@@ -436,18 +436,26 @@ __global__ void __launch_bounds__(256) linear_bwd_w_kernel(const float* __restri
     if (k == 0 && db != nullptr) db[m] += accb;
 }
 
+// one block per (n, 32 input features): 8 thread groups stride over the M outputs (coalesced along k), tree-add
 __global__ void __launch_bounds__(256) linear_bwd_x_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                            const float* __restrict__ dy, int64_t dy_ld,
                                                            float* __restrict__ dx, int64_t N, int64_t K, int64_t M,
                                                            int act_in, int accumulate) {
     pdl_prologue();
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= N * K) return;
-    const int64_t n = idx / K, k = idx % K;
+    __shared__ float part[8][32];
+    const int c = threadIdx.x & 31, lane = threadIdx.x >> 5;
+    const int64_t n = blockIdx.y;
+    const int64_t k = (int64_t)blockIdx.x * 32 + c;
     float acc = 0.f;
-    for (int64_t m = 0; m < M; ++m) acc = fmaf(dy[n * dy_ld + m], W[m * K + k], acc);
-    acc *= act_grad(x[idx], act_in);
-    dx[idx] = accumulate ? dx[idx] + acc : acc;
+    if (k < K)
+        for (int64_t m = lane; m < M; m += 8) acc = fmaf(dy[n * dy_ld + m], W[m * K + k], acc);
+    part[lane][c] = acc;
+    __syncthreads();
+    if (lane == 0 && k < K) {
+        float v = ((part[0][c] + part[1][c]) + (part[2][c] + part[3][c])) + ((part[4][c] + part[5][c]) + (part[6][c] + part[7][c]));
+        v *= act_grad(x[n * K + k], act_in);
+        dx[n * K + k] = accumulate ? dx[n * K + k] + v : v;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -624,7 +632,7 @@ extern "C" int fcwdm_linear_bwd(const float* x, const float* W, const float* dy,
         FCWDM_CHECK_LAUNCH("fcwdm_linear_bwd (dW)");
     }
     if (dx != nullptr) {
-        launch_k(linear_bwd_x_kernel, dim3((unsigned)((N * K + 255) / 256)), dim3(256), 0, st, x, W, dy, dy_ld, dx, N, K, M,
+        launch_k(linear_bwd_x_kernel, dim3((unsigned)((K + 31) / 32), (unsigned)N), dim3(256), 0, st, x, W, dy, dy_ld, dx, N, K, M,
                  act_in, accumulate_dx);
         FCWDM_CHECK_LAUNCH("fcwdm_linear_bwd (dx)");
     }

@@ -160,7 +160,11 @@ def test_fused_adamw_training_reduces_loss(golden):
             for key in g.files:
                 if key.startswith("stepped/"):
                     name = key[len("stepped/"):]
-                    # Adam's first step is ~lr*sign(g): compare where the gradient is well above the bf16 noise
+                    # Adam's first step is ~lr*sign(g): compare where the gradient is well above the bf16 noise; skip
+                    # parameters whose true gradient is zero (a bias in front of a 1-channel-per-group GroupNorm:
+                    # the reference's own value there is fp32 rounding noise whose sign Adam amplifies to +-lr)
+                    if float(np.abs(g["grad/" + name]).max()) < 1e-6:
+                        continue
                     mask = np.abs(g["grad/" + name]) > 0.1 * np.abs(g["grad/" + name]).max()
                     got = params[name].detach().cpu().numpy()
                     np.testing.assert_allclose(got[mask], g[key][mask], atol=3e-4, err_msg=name)
