@@ -20,6 +20,8 @@
 //   * the epilogue (warps 4-7) drains the accumulators with tcgen05.ld, adds bias (+ per-(n,c) timestep
 //     embedding) (+ residual), converts to bf16 and stores channels-last; a second TMEM accumulator stage lets
 //     it overlap the next tile's MMAs.
+#include <stdlib.h>
+
 #include "tc_ptx.cuh"
 
 namespace fcwdm {
@@ -42,6 +44,7 @@ struct ConvArgs {
     long long y_ld;
     double* gn_stats;   // [N][FCWDM_GN_STAT_REPLICAS][gn_groups][2] (pre-zeroed by the caller) or null
     int gn_cpg, gn_groups;
+    int a_slots, b_stages;   // runtime split of shared memory between the halo-plane ring and the weight-tile ring
 };
 
 template <int N_TILE, int TD, int KS>
@@ -54,17 +57,15 @@ struct ConvCfg {
     static constexpr int SLOT_BYTES = (PLANE_BYTES + 1023) / 1024 * 1024;
     static constexpr int PLANES = TD + 2 * PAD;
     static constexpr int B_BYTES = N_TILE * 128;
-    static constexpr int B_STAGES = (N_TILE >= 128) ? 3 : 4;
-    static constexpr int SMEM_BUDGET = 227 * 1024 - 3072;  // 1 KB alignment slack + 1 KB barriers + 1 KB GN statistics
-    static constexpr int A_SLOTS_RAW = (SMEM_BUDGET - B_STAGES * B_BYTES) / SLOT_BYTES;
-    static constexpr int A_SLOTS = A_SLOTS_RAW > 12 ? 12 : A_SLOTS_RAW;
+    static constexpr int SMEM_BUDGET = 227 * 1024 - 3072;  // 1 KB alignment slack + 1 KB barriers/bias + 1 KB GN statistics
+    static constexpr int MAX_A_SLOTS = 12, MAX_B_STAGES = 16;   // barrier area: 8*(2*12 + 2*16 + 4) + 4 = 484 B < 512
     static constexpr int ACC_COLS = TD * N_TILE;
     static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
     static constexpr int TMEM_RAW = ACC_STAGES * ACC_COLS;
     static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : TMEM_RAW <= 64 ? 64 : TMEM_RAW <= 128 ? 128 : TMEM_RAW <= 256 ? 256 : 512;
-    static constexpr int SMEM_BYTES = 1024 + A_SLOTS * SLOT_BYTES + B_STAGES * B_BYTES + 2048;
+    static constexpr int SMEM_BYTES = 227 * 1024;       // always the full carve-out; the rings are sized at launch
     static constexpr int CHUNK = 16;                     // accumulator columns per tcgen05.ld
-    static_assert(A_SLOTS >= TD + 1, "not enough plane slots");
+    static_assert(SMEM_BUDGET >= (PLANES + 1) * SLOT_BYTES + 2 * B_BYTES, "tile does not fit shared memory");
     static_assert(ACC_COLS <= 512, "accumulators exceed tensor memory");
     static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "invalid UMMA N");
 };
@@ -170,15 +171,16 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
     using Cfg = ConvCfg<N_TILE, TD, KS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t A_SLOTS = (uint32_t)args.a_slots, B_STAGES = (uint32_t)args.b_stages;
     const uint32_t smem_a = smem_base;
-    const uint32_t smem_b = smem_a + Cfg::A_SLOTS * Cfg::SLOT_BYTES;
-    const uint32_t bars = smem_b + Cfg::B_STAGES * Cfg::B_BYTES;
+    const uint32_t smem_b = smem_a + A_SLOTS * Cfg::SLOT_BYTES;
+    const uint32_t bars = smem_b + B_STAGES * Cfg::B_BYTES;
     // barrier layout (8 B each)
     const uint32_t full_a = bars;
-    const uint32_t empty_a = full_a + 8 * Cfg::A_SLOTS;
-    const uint32_t full_b = empty_a + 8 * Cfg::A_SLOTS;
-    const uint32_t empty_b = full_b + 8 * Cfg::B_STAGES;
-    const uint32_t tmem_full = empty_b + 8 * Cfg::B_STAGES;
+    const uint32_t empty_a = full_a + 8 * A_SLOTS;
+    const uint32_t full_b = empty_a + 8 * A_SLOTS;
+    const uint32_t empty_b = full_b + 8 * B_STAGES;
+    const uint32_t tmem_full = empty_b + 8 * B_STAGES;
     const uint32_t tmem_empty = tmem_full + 8 * Cfg::ACC_STAGES;
     const uint32_t tmem_slot = tmem_empty + 8 * Cfg::ACC_STAGES;   // 4 B: TMEM base address
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -189,11 +191,11 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < Cfg::A_SLOTS; ++i) {
+        for (int i = 0; i < A_SLOTS; ++i) {
             mbar_init(full_a + 8 * i, 1);
             mbar_init(empty_a + 8 * i, 1);
         }
-        for (int i = 0; i < Cfg::B_STAGES; ++i) {
+        for (int i = 0; i < B_STAGES; ++i) {
             mbar_init(full_b + 8 * i, 1);
             mbar_init(empty_b + 8 * i, 1);
         }
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
                 const TileCoord tc = decode_tile(tile, args, TD, N_TILE);
                 for (int cb = 0; cb < args.n_cb; ++cb) {
                     for (int p = 0; p < Cfg::PLANES; ++p, ++q) {
-                        const uint32_t slot = q % Cfg::A_SLOTS, ph = (q / Cfg::A_SLOTS) & 1;
+                        const uint32_t slot = q % A_SLOTS, ph = (q / A_SLOTS) & 1;
                         mbar_wait(empty_a + 8 * slot, ph ^ 1);
                         mbar_arrive_expect_tx(full_a + 8 * slot, Cfg::PLANE_BYTES);
                         tma_load_5d(smem_a + slot * Cfg::SLOT_BYTES, &map_a, full_a + 8 * slot, cb * 64,
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
                 const TileCoord tc = decode_tile(tile, args, TD, N_TILE);
                 for (int cb = 0; cb < args.n_cb; ++cb) {
                     for (int tap = 0; tap < Cfg::TAPS; ++tap, ++r) {
-                        const uint32_t st = r % Cfg::B_STAGES, ph = (r / Cfg::B_STAGES) & 1;
+                        const uint32_t st = r % B_STAGES, ph = (r / B_STAGES) & 1;
                         mbar_wait(empty_b + 8 * st, ph ^ 1);
                         mbar_arrive_expect_tx(full_b + 8 * st, Cfg::B_BYTES);
                         tma_load_3d(smem_b + st * Cfg::B_BYTES, &map_b, full_b + 8 * st, cb * 64, tc.n0, tap);
@@ -269,18 +271,18 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
                 for (int kd = 0; kd < KS; ++kd) {
                     while (planes_ready < kd + TD) {
                         const uint32_t qq = q_base + planes_ready;
-                        mbar_wait(full_a + 8 * (qq % Cfg::A_SLOTS), (qq / Cfg::A_SLOTS) & 1);
+                        mbar_wait(full_a + 8 * (qq % A_SLOTS), (qq / A_SLOTS) & 1);
                         ++planes_ready;
                     }
                     // descriptors of the TD planes this kd touches (start-address field is in 16-byte units)
                     uint64_t a_desc[TD];
 #pragma unroll
                     for (int j = 0; j < TD; ++j)
-                        a_desc[j] = a_desc_base + (uint64_t)((((q_base + kd + j) % Cfg::A_SLOTS) * Cfg::SLOT_BYTES) >> 4);
+                        a_desc[j] = a_desc_base + (uint64_t)((((q_base + kd + j) % A_SLOTS) * Cfg::SLOT_BYTES) >> 4);
                     for (int kh = 0; kh < KS; ++kh) {
                         for (int kw = 0; kw < KS; ++kw, ++r) {
-                            const uint32_t st = r % Cfg::B_STAGES;
-                            mbar_wait(full_b + 8 * st, (r / Cfg::B_STAGES) & 1);
+                            const uint32_t st = r % B_STAGES;
+                            mbar_wait(full_b + 8 * st, (r / B_STAGES) & 1);
                             tc_fence_after();
                             if (elect_one()) {
                                 const uint64_t b_desc = b_desc_base + (uint64_t)((st * Cfg::B_BYTES) >> 4);
@@ -300,11 +302,11 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
                         }
                     }
                     // plane kd is not needed by later taps of this channel block
-                    if (elect_one()) umma_commit(empty_a + 8 * ((q_base + kd) % Cfg::A_SLOTS));
+                    if (elect_one()) umma_commit(empty_a + 8 * ((q_base + kd) % A_SLOTS));
                     __syncwarp();
                 }
                 if (elect_one()) {
-                    for (int p = KS; p < Cfg::PLANES; ++p) umma_commit(empty_a + 8 * ((q_base + p) % Cfg::A_SLOTS));
+                    for (int p = KS; p < Cfg::PLANES; ++p) umma_commit(empty_a + 8 * ((q_base + p) % A_SLOTS));
                 }
                 __syncwarp();
                 q_base += Cfg::PLANES;
@@ -488,6 +490,21 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, ConvArgs a,
     FCWDM_REQUIRE(tiles < (1ll << 31), FCWDM_ERR_UNSUPPORTED, "fcwdm_conv3d_fwd: too many tiles");
     a.num_tiles = (int)tiles;
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    // shared-memory split: the weight ring must cover the L2 round trip of one tile's weight stream (bytes in flight =
+    // consumption rate x latency, ~64-96 KB); the halo-plane ring gets the rest (>= one tile's planes + 1 for overlap)
+    {
+        static const int env_b = getenv("FCWDM_CONV_BSTAGES") ? atoi(getenv("FCWDM_CONV_BSTAGES")) : 0;
+        static const int env_a = getenv("FCWDM_CONV_ASLOTS") ? atoi(getenv("FCWDM_CONV_ASLOTS")) : 0;
+        int b = env_b > 0 ? env_b : (N_TILE >= 128 ? 5 : 10);
+        if (b > Cfg::MAX_B_STAGES) b = Cfg::MAX_B_STAGES;
+        while (b > 2 && (Cfg::SMEM_BUDGET - b * Cfg::B_BYTES) / Cfg::SLOT_BYTES < Cfg::PLANES + 1) --b;
+        int as = (Cfg::SMEM_BUDGET - b * Cfg::B_BYTES) / Cfg::SLOT_BYTES;
+        if (env_a > 0 && env_a < as) as = env_a;
+        if (as > Cfg::MAX_A_SLOTS) as = Cfg::MAX_A_SLOTS;
+        if (as < TD + 1) as = TD + 1;
+        a.a_slots = as;
+        a.b_stages = b;
+    }
     launch_k(conv3d_igemm_kernel<N_TILE, TD, KS>, dim3(grid), dim3(256), Cfg::SMEM_BYTES, st, ma, mb, a);
     FCWDM_CHECK_LAUNCH("fcwdm_conv3d_fwd");
     return FCWDM_OK;
