@@ -91,6 +91,19 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def ncu_traffic(name):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary (profiles/)."""
+    path = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(path):
+        return None
+    tot = 0.0
+    for line in open(path):
+        parts = line.split()
+        if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and parts[1] == "Mbyte":
+            tot += float(parts[2]) * 1e6
+    return tot or None
+
+
 def build_model(device):
     from guided_diffusion.script_util import create_model_and_diffusion, model_and_diffusion_defaults
     args = model_and_diffusion_defaults()
@@ -376,7 +389,9 @@ def run_gpu(args):
         ms_k, flop = time_dominant_kernel(device)
         ach = flop / (ms_k * 1e-3) / 1e12
         result["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                              "frac": ach / peaks["tf_burst"], "traffic": None,
+                              "frac": ach / peaks["tf_burst"], "traffic": ncu_traffic("r01_conv_pair64_ncu.txt"),
+                              "traffic_note": "dram__bytes_read+write of one launch, ncu --set full (profiles/"
+                                              "r01_conv_pair64_ncu.txt); algorithmic 257 MB",
                               "kernel": "conv3d_pair_kernel<64> (cta_group::2, kd-fused) 64->64 @112x112x80",
                               "us_per_launch": ms_k * 1e3, "flop_per_launch": flop}
         hb = time_haar(device)
@@ -435,6 +450,7 @@ def run_train(args):
     peaks = measured_peaks()
     model, diffusion = build_model(device)
     model.train()
+    diffusion.sync_timestep_check = False        # validate t on the device: no host read-back stalling the launch queue
     sync = None
     if world > 1:
         ddp.broadcast_parameters(model)

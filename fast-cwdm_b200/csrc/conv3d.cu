@@ -56,7 +56,8 @@ struct ConvCfg {
     static constexpr int PLANE_BYTES = HROWS * ROWP * 128;
     static constexpr int SLOT_BYTES = (PLANE_BYTES + 1023) / 1024 * 1024;
     static constexpr int PLANES = TD + 2 * PAD;
-    static constexpr int B_BYTES = N_TILE * 128;
+    static constexpr int B_TAP_BYTES = N_TILE * 128;        // one tap's [N_TILE x 64] weight tile
+    static constexpr int B_BYTES = KS * B_TAP_BYTES;         // one weight stage = the KS kw-taps of one (kd, kh): one TMA, one barrier round
     static constexpr int SMEM_BUDGET = 227 * 1024 - 3072;  // 1 KB alignment slack + 1 KB barriers/bias + 1 KB GN statistics
     static constexpr int MAX_A_SLOTS = 12, MAX_B_STAGES = 16;   // barrier area: 8*(2*12 + 2*16 + 4) + 4 = 484 B < 512
     static constexpr int ACC_COLS = TD * N_TILE;
@@ -65,7 +66,7 @@ struct ConvCfg {
     static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : TMEM_RAW <= 64 ? 64 : TMEM_RAW <= 128 ? 128 : TMEM_RAW <= 256 ? 256 : 512;
     static constexpr int SMEM_BYTES = 227 * 1024;       // always the full carve-out; the rings are sized at launch
     static constexpr int CHUNK = 16;                     // accumulator columns per tcgen05.ld
-    static_assert(SMEM_BUDGET >= (PLANES + 1) * SLOT_BYTES + 2 * B_BYTES, "tile does not fit shared memory");
+    static_assert(SMEM_BUDGET >= (TD + 1) * SLOT_BYTES + 2 * B_BYTES, "tile does not fit shared memory");
     static_assert(ACC_COLS <= 512, "accumulators exceed tensor memory");
     static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "invalid UMMA N");
 };
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
             for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
                 const TileCoord tc = decode_tile(tile, args, TD, N_TILE);
                 for (int cb = 0; cb < args.n_cb; ++cb) {
-                    for (int tap = 0; tap < Cfg::TAPS; ++tap, ++r) {
+                    for (int tap = 0; tap < Cfg::TAPS; tap += KS, ++r) {
                         const uint32_t st = r % B_STAGES, ph = (r / B_STAGES) & 1;
                         mbar_wait(empty_b + 8 * st, ph ^ 1);
                         mbar_arrive_expect_tx(full_b + 8 * st, Cfg::B_BYTES);
@@ -279,13 +280,14 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
 #pragma unroll
                     for (int j = 0; j < TD; ++j)
                         a_desc[j] = a_desc_base + (uint64_t)((((q_base + kd + j) % A_SLOTS) * Cfg::SLOT_BYTES) >> 4);
-                    for (int kh = 0; kh < KS; ++kh) {
-                        for (int kw = 0; kw < KS; ++kw, ++r) {
-                            const uint32_t st = r % B_STAGES;
-                            mbar_wait(full_b + 8 * st, (r / B_STAGES) & 1);
-                            tc_fence_after();
-                            if (elect_one()) {
-                                const uint64_t b_desc = b_desc_base + (uint64_t)((st * Cfg::B_BYTES) >> 4);
+                    for (int kh = 0; kh < KS; ++kh, ++r) {
+                        const uint32_t st = r % B_STAGES;
+                        mbar_wait(full_b + 8 * st, (r / B_STAGES) & 1);
+                        tc_fence_after();
+                        if (elect_one()) {
+#pragma unroll
+                            for (int kw = 0; kw < KS; ++kw) {
+                                const uint64_t b_desc = b_desc_base + (uint64_t)((st * Cfg::B_BYTES + kw * Cfg::B_TAP_BYTES) >> 4);
                                 const uint64_t tap_off = (uint64_t)(((kh * Cfg::ROWP + kw) * 128) >> 4);
                                 const uint32_t first = ((cb == 0) && (kd == 0) && (kh == 0) && (kw == 0)) ? 0u : 1u;
 #pragma unroll
@@ -296,10 +298,10 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
                                     umma_bf16(acc0 + j * N_TILE, ad + 4, b_desc + 4, idesc, 1u);
                                     umma_bf16(acc0 + j * N_TILE, ad + 6, b_desc + 6, idesc, 1u);
                                 }
-                                umma_commit(empty_b + 8 * st);   // weight stage free once these MMAs retire
                             }
-                            __syncwarp();
+                            umma_commit(empty_b + 8 * st);   // weight stage (KS taps) free once these MMAs retire
                         }
+                        __syncwarp();
                     }
                     // plane kd is not needed by later taps of this channel block
                     if (elect_one()) umma_commit(empty_a + 8 * ((q_base + kd) % A_SLOTS));
@@ -495,7 +497,7 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, ConvArgs a,
     {
         static const int env_b = getenv("FCWDM_CONV_BSTAGES") ? atoi(getenv("FCWDM_CONV_BSTAGES")) : 0;
         static const int env_a = getenv("FCWDM_CONV_ASLOTS") ? atoi(getenv("FCWDM_CONV_ASLOTS")) : 0;
-        int b = env_b > 0 ? env_b : (N_TILE >= 128 ? 5 : 10);
+        int b = env_b > 0 ? env_b : (KS == 1 ? 8 : (N_TILE >= 128 ? 2 : 4));      // stages of KS taps each
         if (b > Cfg::MAX_B_STAGES) b = Cfg::MAX_B_STAGES;
         while (b > 2 && (Cfg::SMEM_BUDGET - b * Cfg::B_BYTES) / Cfg::SLOT_BYTES < Cfg::PLANES + 1) --b;
         int as = (Cfg::SMEM_BUDGET - b * Cfg::B_BYTES) / Cfg::SLOT_BYTES;
@@ -588,7 +590,7 @@ extern "C" int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, con
     auto encode_b = [&](int n_tile) -> int {
         cuuint64_t dims[3] = {(cuuint64_t)cin_p, (cuuint64_t)cout_p, (cuuint64_t)taps};
         cuuint64_t strides[2] = {(cuuint64_t)cin_p * 2, (cuuint64_t)cout_p * cin_p * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)n_tile, 1};
+        cuuint32_t box[3] = {64, (cuuint32_t)n_tile, (cuuint32_t)ksize};   // the ksize kw-taps of one (kd, kh) per load
         cuuint32_t es[3] = {1, 1, 1};
         CUresult r = g_encode(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wp), dims, strides, box, es,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -42,6 +42,7 @@ class WavUNetEngine:
         # statistics pass in round 1, so opt-in
         self.fuse_stats = os.environ.get("FCWDM_FUSED_STATS", "0") == "1"          # single-CTA kernel: opt-in
         self.fuse_stats_pair = os.environ.get("FCWDM_NO_FUSED_STATS_PAIR", "0") != "1"  # pair kernel: register sums, free
+        self.fuse_stats_rows = int(os.environ.get("FCWDM_FUSED_STATS_ROWS", "20000"))   # <= 28x28x20 voxels per batch
         self.use_pair = os.environ.get("FCWDM_NO_PAIR", "0") != "1"
         self.fuse_gn_in = os.environ.get("FCWDM_NO_FUSED_GN_IN", "0") != "1"
 
@@ -120,7 +121,10 @@ class WavUNetEngine:
         stats = None
         cpg = pk.cout // stats_groups if stats_groups and pk.cout % stats_groups == 0 else 0
         ok_pair = pk.pair and self.fuse_stats_pair and cpg and cpg % 2 == 0
-        ok_single = (not pk.pair) and self.fuse_stats and (cpg in (1, 2, 4) or (cpg and cpg % 8 == 0))
+        # single-CTA kernel: break-even against the separate (HBM-roofline) statistics pass on large tensors, but on the
+        # low-resolution layers the statistics pass is a latency-bound launch of its own -> fuse there
+        ok_single = (not pk.pair) and (self.fuse_stats or rows <= self.fuse_stats_rows) and \
+            (cpg in (1, 2, 4) or (cpg and cpg % 8 == 0))
         if stats_groups and stats_groups <= 32 and (ok_pair or ok_single):
             stats = self._stats_slot(N, stats_groups, x.device)
             self._stats[id(y)] = (stats, stats_groups, y)     # holding y keeps its id unique until consumed

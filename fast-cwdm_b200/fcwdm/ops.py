@@ -30,19 +30,32 @@ def _need_cuda(t, what):
 
 class _on:
     """Make `dev` current for the launch (the reference's .cuda() used the *current* device,
-    DWT_IDWT_layer.py:505-511; here the input's device decides) and make sure the library is initialised."""
+    DWT_IDWT_layer.py:505-511; here the input's device decides) and make sure the library is initialised.
+    Fast path (every launch of a training / sampling step goes through here): when `dev` already is the current
+    device and the library is initialised for it, no guard object is created."""
+
+    __slots__ = ("dev", "guard")
 
     def __init__(self, dev):
         self.dev = dev
-        self.guard = torch.cuda.device(dev)
+        self.guard = None
 
     def __enter__(self):
-        self.guard.__enter__()
-        native.init(self.dev.index if self.dev.index is not None else torch.cuda.current_device())
-        return _stream(self.dev)
+        idx = self.dev.index
+        cur = torch.cuda.current_device()
+        if idx is None:
+            idx = cur
+        if idx != cur:
+            self.guard = torch.cuda.device(self.dev)
+            self.guard.__enter__()
+        if idx not in native._inited_devices:
+            native.init(idx)
+        return _VP(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def __exit__(self, *a):
-        return self.guard.__exit__(*a)
+        if self.guard is not None:
+            return self.guard.__exit__(*a)
+        return False
 
 
 def _dtype_code(t):

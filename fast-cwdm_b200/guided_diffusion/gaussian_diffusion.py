@@ -156,9 +156,19 @@ class GaussianDiffusion:
             self._dev_tables[key] = tab
         return tab
 
+    sync_timestep_check = True
+
     def _check_t(self, t):
-        """Reference :1257-1259 raises IndexError for out-of-range timesteps."""
-        if t.numel() and (int(t.min()) < 0 or int(t.max()) >= self.num_timesteps):
+        """Reference :1257-1259 raises IndexError for out-of-range timesteps (its `.min()/.max()` read-back is a host
+        synchronisation per call).  With ``sync_timestep_check = False`` (training loops that must not stall the launch
+        queue: fcwdm bench / TrainLoop) CUDA timesteps are validated on the device instead: an out-of-range value
+        trips an asynchronous device-side assert rather than an IndexError."""
+        if not t.numel():
+            return
+        if t.is_cuda and (not self.sync_timestep_check or th.cuda.is_current_stream_capturing()):
+            th._assert_async(((t >= 0) & (t < self.num_timesteps)).all())
+            return
+        if int(t.min()) < 0 or int(t.max()) >= self.num_timesteps:
             raise IndexError(f"Timesteps out of bounds: min={int(t.min())}, max={int(t.max())}, "
                              f"arr len={self.num_timesteps}")
 
