@@ -22,9 +22,10 @@ __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __nv_bfloa
     float* chs = sm + 16 * kNormThreads;
     const int C8 = C >> 3;
     const int n = blockIdx.y;
+    const int nthr = blockDim.x;           // the largest multiple of C/8 that fits kNormThreads
     const int chunk = threadIdx.x % C8;
     const int lane = threadIdx.x / C8;
-    const int vpb = kNormThreads / C8;
+    const int vpb = nthr / C8;
     float s[8], q[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __nv_bfloa
         part[(8 + j) * kNormThreads + threadIdx.x] = q[j];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += kNormThreads) {
+    for (int i = threadIdx.x; i < 2 * C; i += nthr) {
         const int comp = i / C, c = i % C;
         const float* p = part + (comp * 8 + (c & 7)) * kNormThreads + (c >> 3);
         float a = 0.f;
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(kNormThreads) gn_stats_kernel(const __nv_bfloa
     __syncthreads();
     const int cpg = C / G;
     double* dst = stats + (((int64_t)n * kStatReplicas + (blockIdx.x % kStatReplicas)) * G) * 2;
-    for (int g = threadIdx.x; g < G; g += kNormThreads) {
+    for (int g = threadIdx.x; g < G; g += nthr) {
         double a = 0.0, b = 0.0;
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
             a += (double)chs[c];
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __nv_bfloa
     const int n = blockIdx.y;
     const int cpg = C / G;
     const double cnt = (double)S * (double)cpg;
-    for (int c = threadIdx.x; c < C; c += kNormThreads) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
         double sum = 0.0, sq = 0.0;
         for (int r = 0; r < kStatReplicas; ++r) {
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(kNormThreads) gn_apply_kernel(const __nv_bfloa
     const int C8 = C >> 3;
     const int chunk = threadIdx.x % C8;
     const int lane = threadIdx.x / C8;
-    const int vpb = kNormThreads / C8;
+    const int vpb = blockDim.x / C8;
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -169,8 +170,8 @@ using namespace fcwdm;
 static int gn_check(const char* fn, int64_t N, int64_t S, int64_t C, int64_t G) {
     FCWDM_REQUIRE(N >= 0 && S >= 0 && C > 0 && G > 0 && N <= 65535, FCWDM_ERR_INVALID, "%s: bad dimension", fn);
     FCWDM_REQUIRE(C % G == 0, FCWDM_ERR_INVALID, "%s: C (%lld) not divisible by G (%lld)", fn, (long long)C, (long long)G);
-    FCWDM_REQUIRE(C % 8 == 0 && (kNormThreads % (C / 8)) == 0 && C <= 2048, FCWDM_ERR_UNSUPPORTED,
-                  "%s: C must be 8 * a divisor of %d (got %lld)", fn, kNormThreads, (long long)C);
+    FCWDM_REQUIRE(C % 8 == 0 && C <= 2048, FCWDM_ERR_UNSUPPORTED, "%s: C must be a multiple of 8, at most 2048 (got %lld)",
+                  fn, (long long)C);
     return FCWDM_OK;
 }
 
@@ -186,12 +187,13 @@ extern "C" int fcwdm_groupnorm_stats(const void* x, int64_t ld, double* stats, i
     FCWDM_REQUIRE(e == cudaSuccess, FCWDM_ERR_CUDA, "fcwdm_groupnorm_stats: memset failed (%s)", cudaGetErrorString(e));
     if (S == 0) return FCWDM_OK;
     const int64_t vpb = kNormThreads / (C / 8);
+    const unsigned nthr = (unsigned)(vpb * (C / 8));  // 256, or e.g. 240 for C = 192 / 384 (the plain U-Net's concatenated skips)
     int64_t blocks = (S + vpb * 4 - 1) / (vpb * 4);  // >= 4 voxels per thread
     const int64_t cap = (int64_t)num_sms() * 8 / (N > 8 ? 8 : N);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     dim3 grid((unsigned)blocks, (unsigned)N);
-    launch_k(gn_stats_kernel, dim3(grid), dim3(kNormThreads), (16 * kNormThreads + 2 * C) * sizeof(float), st, (const __nv_bfloat16*)x, ld, stats, S, (int)C,
+    launch_k(gn_stats_kernel, dim3(grid), dim3(nthr), (16 * kNormThreads + 2 * C) * sizeof(float), st, (const __nv_bfloat16*)x, ld, stats, S, (int)C,
                                                                         (int)G);
     FCWDM_CHECK_LAUNCH("fcwdm_groupnorm_stats");
     return FCWDM_OK;
@@ -207,6 +209,7 @@ extern "C" int fcwdm_groupnorm_apply(const void* x, int64_t x_ld, void* y, int64
                   "fcwdm_groupnorm_apply: bad ld");
     if (N * S == 0) return FCWDM_OK;
     const int64_t vpb = kNormThreads / (C / 8);
+    const unsigned nthr = (unsigned)(vpb * (C / 8));
     int64_t blocks = (S + vpb * 4 - 1) / (vpb * 4);
     const int64_t cap = (int64_t)num_sms() * 8 / (N > 8 ? 8 : N);
     if (blocks > cap) blocks = cap;
@@ -214,10 +217,10 @@ extern "C" int fcwdm_groupnorm_apply(const void* x, int64_t x_ld, void* y, int64
     dim3 grid((unsigned)blocks, (unsigned)N);
     cudaStream_t st = (cudaStream_t)stream;
     if (silu)
-        launch_k(gn_apply_kernel<true>, dim3(grid), dim3(kNormThreads), 2 * C * sizeof(float), st, 
+        launch_k(gn_apply_kernel<true>, dim3(grid), dim3(nthr), 2 * C * sizeof(float), st, 
             (const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)y, y_ld, stats, gamma, beta, S, (int)C, (int)G, eps);
     else
-        launch_k(gn_apply_kernel<false>, dim3(grid), dim3(kNormThreads), 2 * C * sizeof(float), st, 
+        launch_k(gn_apply_kernel<false>, dim3(grid), dim3(nthr), 2 * C * sizeof(float), st, 
             (const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)y, y_ld, stats, gamma, beta, S, (int)C, (int)G, eps);
     FCWDM_CHECK_LAUNCH("fcwdm_groupnorm_apply");
     return FCWDM_OK;

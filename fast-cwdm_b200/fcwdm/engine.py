@@ -74,10 +74,10 @@ class WavUNetEngine:
                 self._conv[id(mod)] = pk
         # all per-ResBlock timestep projections Linear(SiLU(emb)) (wunet.py:203-206,250) as ONE dense layer:
         # rows of W_cat are the concatenated emb_layers[1] weights; a block reads its column slice of the result
-        from guided_diffusion.wunet import ResBlock
         self._emb_off, ws, bs, off = {}, [], [], 0
         for mod in self.model.modules():
-            if isinstance(mod, ResBlock) and id(mod) not in self._emb_off:
+            # every ResBlock of either U-Net (wunet.ResBlock / unet.ResBlock): has in_layers + emb_layers
+            if hasattr(mod, "emb_layers") and hasattr(mod, "in_layers") and id(mod) not in self._emb_off:
                 lin = mod.emb_layers[1]
                 self._emb_off[id(mod)] = (off, lin.out_features)
                 ws.append(lin.weight.detach().float())
@@ -112,12 +112,13 @@ class WavUNetEngine:
             return torch.empty((rows, ld), dtype=torch.bfloat16, device=device)
         return torch.zeros((rows, ld), dtype=torch.bfloat16, device=device)   # pad channels feed zero weights
 
-    def _conv3d(self, mod, x, N, dims, chan_bias=None, residual=None, out_ld=None, stats_groups=0, gn_in=None):
+    def _conv3d(self, mod, x, N, dims, chan_bias=None, residual=None, out_ld=None, stats_groups=0, gn_in=None, out=None):
         """stats_groups > 0: the conv epilogue also produces the GroupNorm statistics of its output (kept in
-        self._stats under the output buffer's id until the consuming GroupNorm picks them up)."""
+        self._stats under the output buffer's id until the consuming GroupNorm picks them up).
+        out: write into this (rows, >= C_out) buffer / column-slice view instead of allocating (zero-copy concat)."""
         pk = self._conv[id(mod)]
         rows = N * dims[0] * dims[1] * dims[2]
-        y = self._buf(rows, pk.cout, x.device, out_ld)
+        y = out if out is not None else self._buf(rows, pk.cout, x.device, out_ld)
         stats = None
         cpg = pk.cout // stats_groups if stats_groups and pk.cout % stats_groups == 0 else 0
         ok_pair = pk.pair and self.fuse_stats_pair and cpg and cpg % 2 == 0

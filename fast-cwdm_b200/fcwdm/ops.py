@@ -415,3 +415,20 @@ def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0)
     with _on(p.device) as st:
         native.call("fcwdm_adamw", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
                     float(eps), float(weight_decay), int(step), float(grad_scale), st)
+
+
+# ----------------------------------------------------------------------------------------------------
+# plain UNetModel resampling (csrc/resample.cu)
+# ----------------------------------------------------------------------------------------------------
+def avgpool2_cl(x, dims, C, y, pool_depth=True):
+    """x (N,D,H,W,C) cl bf16 -> y pooled by 2 in H, W (and D when pool_depth)."""
+    N, D, H, W = dims
+    with _on(x.device) as st:
+        native.call("fcwdm_avgpool2_cl", _ptr(x), x.stride(0), _ptr(y), y.stride(0), N, D, H, W, C, 1 if pool_depth else 0, st)
+
+
+def upsample2_cl(x, dims, C, y, up_depth=True):
+    """nearest-neighbour x2; dims = (N, D, H, W) of the INPUT."""
+    N, D, H, W = dims
+    with _on(x.device) as st:
+        native.call("fcwdm_upsample2_cl", _ptr(x), x.stride(0), _ptr(y), y.stride(0), N, D, H, W, C, 1 if up_depth else 0, st)

@@ -297,7 +297,8 @@ class GaussianDiffusion:
             indices = tqdm(indices)
 
         from .wunet import WavUNetModel
-        fused = (isinstance(inner, WavUNetModel) and img.is_cuda and cond_fn is None and denoised_fn is None
+        from .unet import UNetModel
+        fused = (isinstance(inner, (WavUNetModel, UNetModel)) and hasattr(inner, "engine") and img.is_cuda and cond_fn is None and denoised_fn is None
                  and not model_kwargs and not rescale and shape[1] == 8
                  and self.model_mean_type in (ModelMeanType.START_X, ModelMeanType.EPSILON)
                  and self.model_var_type in (ModelVarType.FIXED_LARGE, ModelVarType.FIXED_SMALL)

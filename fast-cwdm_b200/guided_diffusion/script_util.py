@@ -5,9 +5,8 @@ entry scripts use (scripts/sample.py:19-21,31; scripts/train.py): ``model_and_di
 Same flag names, defaults and meaning.  The classifier / super-resolution factories are out of scope
 (unused by the hot path).
 
-``use_freq=True`` builds this package's WavUNetModel (B200 kernels).  ``use_freq=False`` selects the reference's
-plain ``UNetModel`` (guided_diffusion/unet.py), which is a "next" row: it is imported from an
-unmodified reference checkout when one is on this package's path and runs on stock PyTorch."""
+``use_freq=True`` builds this package's WavUNetModel, ``use_freq=False`` this package's plain ``UNetModel`` (the model
+run.sh ships); both run on the B200 kernels."""
 import argparse
 
 from . import gaussian_diffusion as gd
@@ -91,13 +90,7 @@ def create_model(image_size, num_channels, num_res_blocks, channel_mult="", lear
                   bottleneck_attention=bottleneck_attention, additive_skips=additive_skips)
     if use_freq:
         return WavUNetModel(use_freq=True, **kwargs)
-    try:
-        from .unet import UNetModel   # resolved from the reference checkout through this package's __path__
-    except ImportError as e:
-        raise NotImplementedError(
-            "use_freq=False selects the reference's UNetModel, which is outside this round's hot path "
-            "(SURVEY.md section 8f, next row 1) and needs an unmodified reference checkout at "
-            "$FCWDM_REFERENCE_ROOT to import guided_diffusion/unet.py from") from e
+    from .unet import UNetModel           # this package's fcwdm-backed plain U-Net
     return UNetModel(resample_2d=resample_2d, **kwargs)
 
 

@@ -245,6 +245,16 @@ int fcwdm_linear_bwd(const float* x, const float* W, const float* dy, int64_t dy
 int fcwdm_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                 float weight_decay, int64_t step, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Plain UNetModel resampling (guided_diffusion/unet.py:40-100), channels-last bf16 (N, D, H, W, C), C % 8 == 0.
+ * avgpool: avg_pool_nd(kernel = stride = 2) -- or (1,2,2) when pool_depth == 0 (resample_2d) -- of x (N,D,H,W,C);
+ * upsample: F.interpolate(mode="nearest") by 2 in H and W, and in D when up_depth != 0; (D,H,W) = INPUT dims.
+ * ---------------------------------------------------------------------------------------------------- */
+int fcwdm_avgpool2_cl(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t N, int64_t D, int64_t H, int64_t W,
+                      int64_t C, int pool_depth, void* stream);
+int fcwdm_upsample2_cl(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t N, int64_t D, int64_t H, int64_t W,
+                       int64_t C, int up_depth, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -150,3 +150,22 @@ def test_flag_plumbing_matches_reference_defaults():
     kw = args_to_dict(a, d.keys())
     assert kw["use_freq"] is True and kw["channel_mult"] == "1,2,2,4" and kw["diffusion_steps"] == 10
     assert str2bool("yes") and not str2bool("0")
+
+
+def test_unet_state_dict_matches_reference(golden):
+    """The drop-in plain UNetModel exposes the reference's state-dict keys and shapes (run.sh configuration:
+    channel_mult 1,2,2,4,4, 64 base channels), so released checkpoints load unchanged."""
+    from guided_diffusion.script_util import create_model, model_and_diffusion_defaults
+    g = golden("unet_small")
+    m = create_model(image_size=224, num_channels=64, num_res_blocks=2, channel_mult="1,2,2,4,4", attention_resolutions="",
+                     dims=3, in_channels=32, out_channels=8, bottleneck_attention=False, resblock_updown=True,
+                     resample_2d=False, use_freq=False)
+    assert type(m).__module__ == "guided_diffusion.unet" and type(m).__name__ == "UNetModel"
+    sd = m.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["big_keys"]]
+    assert [",".join(map(str, v.shape)) for v in sd.values()] == [str(s) for s in g["big_shapes"]]
+    assert sum(p.numel() for p in m.parameters()) == int(g["big_n_params"])
+    with pytest.raises(NotImplementedError):
+        create_model(image_size=224, num_channels=64, num_res_blocks=2, channel_mult="1,2", attention_resolutions="",
+                     dims=3, in_channels=32, out_channels=8, bottleneck_attention=False, resblock_updown=False,
+                     use_freq=False)

@@ -168,3 +168,13 @@ def test_training_step_small(golden):
             # rounding noise, so compare only where |g| is far above eps = 1e-8
             mask = np.abs(g["grad/" + name]) > 1e-5
             np.testing.assert_allclose(p.numpy()[mask], g[key][mask], atol=2e-5, err_msg=name)
+
+
+def test_unet_small(golden):
+    """Plain UNetModel (run.sh's use_freq=False model) forward against the reference fixture."""
+    from oracle import unet as ou
+    g = golden("unet_small")
+    shapes = {str(k): tuple(int(v) for v in str(s).split(",")) for k, s in zip(g["keys"], g["shapes"])}
+    sd = ow.seeded_state_dict(shapes, seed=0)
+    y = ou.unet_forward(sd, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), model_channels=32, channel_mult=(1, 2, 2))
+    assert np.abs(y.numpy() - g["y"]).max() < 5e-5 * max(1.0, np.abs(g["y"]).max())
