@@ -104,10 +104,15 @@ def ncu_traffic(name):
     return tot or None
 
 
+CFG_UNET = dict(CFG_W4, use_freq=False, channel_mult="1,2,2,4,4", resample_2d=False)      # run.sh:59-66,109-133
+UNET_FLOP_PER_STEP = 7168.7e9           # SURVEY.md section 8f row 1 [probed]: plain UNetModel, 81.5 M parameters
+MODEL = {"name": "wunet"}
+
+
 def build_model(device):
     from guided_diffusion.script_util import create_model_and_diffusion, model_and_diffusion_defaults
     args = model_and_diffusion_defaults()
-    args.update(CFG_W4)
+    args.update(CFG_UNET if MODEL["name"] == "unet" else CFG_W4)
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
@@ -364,6 +369,7 @@ def run_gpu(args):
     finite = bool(torch.isfinite(out).all())
 
     result = None
+    flop_step = UNET_FLOP_PER_STEP if MODEL["name"] == "unet" else CONV_FLOP_PER_STEP
     if rank == 0:
         vols = args.steps * world * args.batch
         value = vols / (ms_res * 1e-3)
@@ -374,14 +380,16 @@ def run_gpu(args):
             "metric": "sampled 224x224x160 volumes/sec", "value": value, "unit": "volumes/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": f"volumes sharded over {world} GPU(s), no collective",
+            "config": {"workload": WORKLOAD if MODEL["name"] == "wunet" else WORKLOAD.replace(
+                           "WavUNetModel CFG-W4 (1,2,2,4)", "plain UNetModel (run.sh: 1,2,2,4,4, resample_2d=False)"),
+                       "parallelism": f"volumes sharded over {world} GPU(s), no collective",
                        "l2": "per-step activations ~10 GB >> 126 MB L2 (no flush needed)", "T": T_STEPS, "volumes_per_step": args.batch,
-                       "denoiser_gflop_per_step": CONV_FLOP_PER_STEP / 1e9, "peaks": peaks["src"],
+                       "denoiser_gflop_per_step": flop_step / 1e9, "peaks": peaks["src"],
                        "output_finite": finite},
             "e2e": {"value": e2e, "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_volume * args.steps),
             "clocks": clk,
-            "step_tflops": CONV_FLOP_PER_STEP * T_STEPS * vols / (ms_res * 1e-3) / 1e12,
+            "step_tflops": flop_step * T_STEPS * vols / (ms_res * 1e-3) / 1e12,
         }
     if world > 1:
         dist.barrier()
@@ -398,7 +406,7 @@ def run_gpu(args):
         result["secondary"] = {"dwt3d_gbs": hb["dwt3d"], "idwt3d_gbs": hb["idwt3d"], "hbm_peak_gbs": peaks["hbm"],
                                "dwt3d_frac": hb["dwt3d"] / peaks["hbm"], "idwt3d_frac": hb["idwt3d"] / peaks["hbm"],
                                "workload": "16 x 224x224x160 fp32 planar, 2*numel*4 bytes per launch"}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and MODEL["name"] == "wunet":
             result["cpu_baseline"] = cpu_baseline()
         else:
             result["cpu_baseline"] = None
@@ -554,9 +562,12 @@ def main():
     ap.add_argument("--impl", default="fcwdm", choices=["fcwdm", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=1, help="volumes per GPU per step (BASELINE config 3 uses 8)")
+    ap.add_argument("--model", default="wunet", choices=["wunet", "unet"],
+                    help="wunet = WavUNetModel CFG-W4 (the headline); unet = the plain UNetModel of run.sh (1,2,2,4,4)")
     ap.add_argument("--workload", default="sample", choices=["sample", "train"],
                     help="sample = BASELINE config 2/3 (the headline, default); train = config 4 training step")
     args = ap.parse_args()
+    MODEL["name"] = args.model
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "train":
