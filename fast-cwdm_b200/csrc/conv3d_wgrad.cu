@@ -258,6 +258,36 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
     }
 }
 
+// Few splits (the low-resolution layers, where the output-channel blocks already fill the GPU): one block = one output
+// channel x 32 input channels x all taps; coalesced reads along ci, shared-memory transpose, coalesced writes of the
+// 32 x taps contiguous floats.
+__global__ void __launch_bounds__(256) wgrad_finalize_small_kernel(const float* __restrict__ ws, float* __restrict__ dw,
+                                                                   int n_split, int taps, int Cout, int Cin, int co_p,
+                                                                   int ci_p, int accumulate) {
+    pdl_prologue();
+    __shared__ float tile[27][33];
+    const int co = blockIdx.y;
+    const int cib = blockIdx.x * 32;
+    const size_t split_stride = (size_t)taps * co_p * ci_p;
+    for (int i = threadIdx.x; i < taps * 32; i += blockDim.x) {
+        const int tap = i >> 5, c = i & 31;
+        float a = 0.f;
+        if (cib + c < Cin) {
+            const float* p = ws + ((size_t)tap * co_p + co) * ci_p + cib + c;
+            for (int sp = 0; sp < n_split; ++sp) a += p[sp * split_stride];
+        }
+        tile[tap][c] = a;
+    }
+    __syncthreads();
+    const int n_ci = (Cin - cib) < 32 ? (Cin - cib) : 32;
+    float* out = dw + ((size_t)co * Cin + cib) * taps;
+    for (int i = threadIdx.x; i < n_ci * taps; i += blockDim.x) {
+        const int c = i / taps, tap = i % taps;
+        const float v = tile[tap][c];
+        out[i] = accumulate ? out[i] + v : v;
+    }
+}
+
 // (Cout, Cin, k^3) f32 -> (Cin, Cout, k^3) f32 with the taps reversed: the data-gradient of a stride-1 "same"
 // convolution is the forward convolution of dY with these weights.
 __global__ void __launch_bounds__(256) transpose_flip_weights_kernel(const float* __restrict__ w, float* __restrict__ wt,
@@ -446,8 +476,12 @@ extern "C" int fcwdm_conv3d_wgrad(const void* x, int64_t x_ld, const void* dy, i
     }
     FCWDM_REQUIRE(rc != FCWDM_ERR_UNSUPPORTED, FCWDM_ERR_UNSUPPORTED, "fcwdm_conv3d_wgrad: no kernel variant for this shape");
     if (rc) return rc;
-    launch_k(wgrad_finalize_kernel, dim3((unsigned)((Cin + 31) / 32), (unsigned)Cout, (unsigned)taps), dim3(256), 0, st,
-             (const float*)workspace, dw, p.n_split, taps, (int)Cout, (int)Cin, p.co_p, p.ci_p, accumulate);
+    if (p.n_split <= 8)
+        launch_k(wgrad_finalize_small_kernel, dim3((unsigned)((Cin + 31) / 32), (unsigned)Cout), dim3(256), 0, st,
+                 (const float*)workspace, dw, p.n_split, taps, (int)Cout, (int)Cin, p.co_p, p.ci_p, accumulate);
+    else
+        launch_k(wgrad_finalize_kernel, dim3((unsigned)((Cin + 31) / 32), (unsigned)Cout, (unsigned)taps), dim3(256), 0, st,
+                 (const float*)workspace, dw, p.n_split, taps, (int)Cout, (int)Cin, p.co_p, p.ci_p, accumulate);
     FCWDM_CHECK_LAUNCH("fcwdm_conv3d_wgrad (finalize)");
     return FCWDM_OK;
 }
@@ -462,5 +496,62 @@ extern "C" int fcwdm_conv3d_transpose_flip_weights(const float* w, float* wt, in
     launch_k(transpose_flip_weights_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, w, wt,
              (int)Cout, (int)Cin, taps);
     FCWDM_CHECK_LAUNCH("fcwdm_conv3d_transpose_flip_weights");
+    return FCWDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One-launch re-packing of every conv weight of a model (after each optimizer step the fp32 master weights change and
+// all bf16 operand copies -- forward and data-gradient forms, single-CTA and CTA-pair layouts -- are rebuilt).
+// ---------------------------------------------------------------------------------------------------
+namespace fcwdm {
+
+struct PackJob {            // mirrored by fcwdm/engine.py (8 x int64)
+    const float* src;       // (Cout_w, Cin_w, taps) f32 master weight
+    __nv_bfloat16* dst;
+    long long O, I;         // output / input channels of the conv being packed (swapped w.r.t. the master for dgrad)
+    long long taps;
+    long long pair;         // 1: CTA-pair layout [kh*3+kw][kd][O_p][64]; 0: [tap][O_p][I_p]
+    long long transposed;   // 1: data-gradient form w'[o][i][tap] = w[i][o][taps-1-tap]
+    long long total;        // packed elements
+};
+
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict__ jobs) {
+    pdl_prologue();
+    const PackJob j = jobs[blockIdx.y];
+    const int O = (int)j.O, I = (int)j.I, taps = (int)j.taps;
+    const int O_p = j.pair ? (O <= 16 ? 16 : 64) : (O + 15) / 16 * 16;
+    const int I_p = j.pair ? 64 : (I + 63) / 64 * 64;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < j.total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % I_p);
+        long long r = idx / I_p;
+        const int o = (int)(r % O_p);
+        r /= O_p;
+        int tap;
+        if (j.pair) {
+            const int kd = (int)(r % 3), t2 = (int)(r / 3);
+            tap = kd * 9 + t2;
+        } else {
+            tap = (int)r;
+        }
+        float v = 0.f;
+        if (o < O && i < I)
+            v = j.transposed ? j.src[((long long)i * O + o) * taps + (taps - 1 - tap)] : j.src[((long long)o * I + i) * taps + tap];
+        j.dst[idx] = __float2bfloat16_rn(v);
+    }
+}
+
+}  // namespace fcwdm
+
+extern "C" int fcwdm_conv3d_pack_all(const void* jobs, int64_t n_jobs, int64_t max_total, void* stream) {
+    FCWDM_REQUIRE(jobs != nullptr || n_jobs == 0, FCWDM_ERR_INVALID, "fcwdm_conv3d_pack_all: null job table");
+    FCWDM_REQUIRE(n_jobs >= 0 && n_jobs <= 65535 && max_total >= 0, FCWDM_ERR_INVALID, "fcwdm_conv3d_pack_all: bad argument");
+    if (n_jobs == 0 || max_total == 0) return FCWDM_OK;
+    long long bx = (max_total + 256 * 8 - 1) / (256 * 8);
+    if (bx > 1024) bx = 1024;
+    if (bx < 1) bx = 1;
+    launch_k(fcwdm::pack_all_kernel, dim3((unsigned)bx, (unsigned)n_jobs), dim3(256), 0, (cudaStream_t)stream,
+             (const fcwdm::PackJob*)jobs);
+    FCWDM_CHECK_LAUNCH("fcwdm_conv3d_pack_all");
     return FCWDM_OK;
 }

@@ -11,7 +11,12 @@ namespace fcwdm {
 constexpr int kTrThreads = 256;
 constexpr int kTrReplicas = FCWDM_GN_STAT_REPLICAS;
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// sigmoid through the hardware tanh (one MUFU op, relative error ~2^-11: far below the bf16 rounding of the gradients)
+__device__ __forceinline__ float sigmoid_f(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+}
 
 // per-channel (scale, shift) of x_hat = x * scale + shift from the (sum, sumsq) statistics of fcwdm_groupnorm_stats
 __device__ __forceinline__ void gn_channel_norm(const double* __restrict__ stats, int n, int g, int G, double cnt,
@@ -72,33 +77,36 @@ __global__ void __launch_bounds__(kTrThreads) gn_bwd_reduce_kernel(const __nv_bf
     const __nv_bfloat16* xb = x + (int64_t)n * S * x_ld + chunk * 8;
     const __nv_bfloat16* db = dy + (int64_t)n * S * dy_ld + chunk * 8;
     const int64_t stride = (int64_t)gridDim.x * vpb;
-    for (int64_t v = (int64_t)blockIdx.x * vpb + lane; v < S; v += 2 * stride) {
-        const bool two = v + stride < S;
-        const uint4 ux0 = ld_stream_u4(xb + v * x_ld), ud0 = ld_stream_u4(db + v * dy_ld);
-        uint4 ux1 = make_uint4(0, 0, 0, 0), ud1 = make_uint4(0, 0, 0, 0);
-        if (two) {
-            ux1 = ld_stream_u4(xb + (v + stride) * x_ld);
-            ud1 = ld_stream_u4(db + (v + stride) * dy_ld);
-        }
+    auto accumulate = [&](const uint4& ux, const uint4& ud) {
+        float fx[8], fd[8];
+        unpack8(ux, fx);
+        unpack8(ud, fd);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            float fx[8], fd[8];
-            unpack8(k ? ux1 : ux0, fx);
-            unpack8(k ? ud1 : ud0, fd);       // zeros for the absent second voxel: contributes nothing
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float h = fmaf(fx[j], xs[j], xh[j]);
-                float dz = fd[j];
-                if (kSilu) {
-                    const float z = fmaf(h, gm[j], bt[j]);
-                    const float s = sigmoid_f(z);
-                    dz *= s * fmaf(z, 1.0f - s, 1.0f);
-                }
-                a[j] += dz;
-                b[j] = fmaf(dz, h, b[j]);
+        for (int j = 0; j < 8; ++j) {
+            const float h = fmaf(fx[j], xs[j], xh[j]);
+            float dz = fd[j];
+            if (kSilu) {
+                const float z = fmaf(h, gm[j], bt[j]);
+                const float sg = sigmoid_f(z);
+                dz *= sg * fmaf(z, 1.0f - sg, 1.0f);
             }
+            a[j] += dz;
+            b[j] = fmaf(dz, h, b[j]);
         }
+    };
+    int64_t v = (int64_t)blockIdx.x * vpb + lane;
+    // 8 independent 128-bit loads in flight per thread (4 voxels of x and dy), then the arithmetic
+    for (; v + 3 * stride < S; v += 4 * stride) {
+        uint4 ux[4], ud[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ux[k] = ld_stream_u4(xb + (v + k * stride) * x_ld);
+            ud[k] = ld_stream_u4(db + (v + k * stride) * dy_ld);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) accumulate(ux[k], ud[k]);
     }
+    for (; v < S; v += stride) accumulate(ld_stream_u4(xb + v * x_ld), ld_stream_u4(db + v * dy_ld));
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -189,26 +197,42 @@ __global__ void __launch_bounds__(kTrThreads) gn_bwd_apply_kernel(const __nv_bfl
     const __nv_bfloat16* ab = acc ? acc + (int64_t)n * S * acc_ld + chunk * 8 : nullptr;
     __nv_bfloat16* ob = dx + (int64_t)n * S * dx_ld + chunk * 8;
     const int64_t stride = (int64_t)gridDim.x * vpb;
-    for (int64_t v = (int64_t)blockIdx.x * vpb + lane; v < S; v += stride) {
+    auto apply = [&](const uint4& ux, const uint4& ud, const uint4& ua, int64_t v) {
         float fx[8], fd[8], fa[8];
-        unpack8(ld_stream_u4(xb + v * x_ld), fx);
-        unpack8(ld_stream_u4(db + v * dy_ld), fd);
-        if (ab != nullptr) unpack8(ld_stream_u4(ab + v * acc_ld), fa);
+        unpack8(ux, fx);
+        unpack8(ud, fd);
+        if (ab != nullptr) unpack8(ua, fa);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float h = fmaf(fx[j], xs[j], xh[j]);
             float dz = fd[j];
             if (kSilu) {
                 const float z = fmaf(h, gm[j], bt[j]);
-                const float s = sigmoid_f(z);
-                dz *= s * fmaf(z, 1.0f - s, 1.0f);
+                const float sg = sigmoid_f(z);
+                dz *= sg * fmaf(z, 1.0f - sg, 1.0f);
             }
             float o = k1[j] * dz - h * k2[j] - k3[j];
             if (ab != nullptr) o += fa[j];
             fd[j] = o;
         }
-        *reinterpret_cast<uint4*>(ob + v * dx_ld) = pack8(fd);
+        st_stream_u4(ob + v * dx_ld, pack8(fd));
+    };
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    int64_t v = (int64_t)blockIdx.x * vpb + lane;
+    for (; v + 3 * stride < S; v += 4 * stride) {          // up to 12 independent 128-bit loads in flight per thread
+        uint4 ux[4], ud[4], ua[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ux[k] = ld_stream_u4(xb + (v + k * stride) * x_ld);
+            ud[k] = ld_stream_u4(db + (v + k * stride) * dy_ld);
+            ua[k] = ab != nullptr ? ld_stream_u4(ab + (v + k * stride) * acc_ld) : zero4;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) apply(ux[k], ud[k], ua[k], v + k * stride);
     }
+    for (; v < S; v += stride)
+        apply(ld_stream_u4(xb + v * x_ld), ld_stream_u4(db + v * dy_ld),
+              ab != nullptr ? ld_stream_u4(ab + v * acc_ld) : zero4, v);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -436,25 +460,29 @@ __global__ void __launch_bounds__(256) linear_bwd_w_kernel(const float* __restri
     if (k == 0 && db != nullptr) db[m] += accb;
 }
 
-// one block per (n, 32 input features): 8 thread groups stride over the M outputs (coalesced along k), tree-add
+// one block per (n, 32 input features, slice of the M outputs): 8 thread groups stride over the slice (coalesced along
+// k), tree-add, then ONE atomic per feature into dx (zeroed by the wrapper unless accumulating); the activation
+// derivative distributes over the partial sums
+constexpr int kLinBwdSlices = 16;
 __global__ void __launch_bounds__(256) linear_bwd_x_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                            const float* __restrict__ dy, int64_t dy_ld,
                                                            float* __restrict__ dx, int64_t N, int64_t K, int64_t M,
-                                                           int act_in, int accumulate) {
+                                                           int act_in) {
     pdl_prologue();
     __shared__ float part[8][32];
     const int c = threadIdx.x & 31, lane = threadIdx.x >> 5;
     const int64_t n = blockIdx.y;
     const int64_t k = (int64_t)blockIdx.x * 32 + c;
+    const int64_t per = (M + gridDim.z - 1) / gridDim.z;
+    const int64_t m0 = (int64_t)blockIdx.z * per, m1 = m0 + per < M ? m0 + per : M;
     float acc = 0.f;
     if (k < K)
-        for (int64_t m = lane; m < M; m += 8) acc = fmaf(dy[n * dy_ld + m], W[m * K + k], acc);
+        for (int64_t m = m0 + lane; m < m1; m += 8) acc = fmaf(dy[n * dy_ld + m], W[m * K + k], acc);
     part[lane][c] = acc;
     __syncthreads();
     if (lane == 0 && k < K) {
         float v = ((part[0][c] + part[1][c]) + (part[2][c] + part[3][c])) + ((part[4][c] + part[5][c]) + (part[6][c] + part[7][c]));
-        v *= act_grad(x[n * K + k], act_in);
-        dx[n * K + k] = accumulate ? dx[n * K + k] + v : v;
+        atomicAdd(dx + n * K + k, v * act_grad(x[n * K + k], act_in));
     }
 }
 
@@ -632,8 +660,13 @@ extern "C" int fcwdm_linear_bwd(const float* x, const float* W, const float* dy,
         FCWDM_CHECK_LAUNCH("fcwdm_linear_bwd (dW)");
     }
     if (dx != nullptr) {
-        launch_k(linear_bwd_x_kernel, dim3((unsigned)((K + 31) / 32), (unsigned)N), dim3(256), 0, st, x, W, dy, dy_ld, dx, N, K, M,
-                 act_in, accumulate_dx);
+        if (!accumulate_dx) {
+            cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * N * K, st);
+            FCWDM_REQUIRE(e == cudaSuccess, FCWDM_ERR_CUDA, "fcwdm_linear_bwd: memset failed (%s)", cudaGetErrorString(e));
+        }
+        const unsigned slices = (unsigned)(M >= 64 * kLinBwdSlices ? kLinBwdSlices : 1);
+        launch_k(linear_bwd_x_kernel, dim3((unsigned)((K + 31) / 32), (unsigned)N, slices), dim3(256), 0, st, x, W, dy, dy_ld, dx,
+                 N, K, M, act_in);
         FCWDM_CHECK_LAUNCH("fcwdm_linear_bwd (dx)");
     }
     return FCWDM_OK;

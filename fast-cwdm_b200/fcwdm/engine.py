@@ -15,7 +15,7 @@ import math
 
 import torch
 
-from . import ops
+from . import native, ops
 from .native import FcwdmError
 
 
@@ -50,28 +50,52 @@ class WavUNetEngine:
     def _signature(self):
         return tuple((id(p), p._version, p.device) for p in self.model.parameters())
 
+    want_dgrad = False      # the training engine also keeps the data-gradient form of every conv weight
+
     def prepare(self, device):
         sig = self._signature()
         if sig == self._sig and self._device == device:
             return
-        self._conv.clear()
         self._f32.clear()
-        for mod in self.model.modules():
-            if isinstance(mod, torch.nn.Conv3d):
+        convs = [m for m in self.model.modules() if isinstance(m, torch.nn.Conv3d)]
+        layout = (str(device), self.want_dgrad, self.use_pair) + tuple(
+            (id(m), m.weight.data_ptr(), tuple(m.weight.shape), m.weight.dtype) for m in convs)
+        if layout != getattr(self, "_layout", None):
+            # (re)build the persistent packed-weight buffers and the one-launch re-pack job table
+            self._conv.clear()
+            self._conv_t = {}
+            jobs, keep = [], []
+            for mod in convs:
                 k = mod.kernel_size[0]
                 if mod.kernel_size != (k, k, k) or k not in (1, 3) or mod.stride != (1, 1, 1) or \
                         mod.padding != (k // 2,) * 3 or mod.groups != 1 or mod.dilation != (1, 1, 1):
                     raise NotImplementedError(f"conv3d configuration not supported by the fcwdm kernel: {mod}")
                 if not mod.weight.is_cuda:
-                    raise FcwdmError("WavUNetModel parameters are on the CPU; call model.to(cuda_device) first "
+                    raise FcwdmError("model parameters are on the CPU; call model.to(cuda_device) first "
                                      "(the fcwdm denoiser has no CPU path)")
-                pk = _Packed()
-                # C_in, C_out <= 64 (the full-resolution layers): kd-fused CTA-pair kernel with resident weights
-                pk.pair = self.use_pair and ops.conv3d_pair_supported(mod.in_channels, mod.out_channels, k)
-                pk.wp = ops.conv3d_pair_pack_weights(mod.weight) if pk.pair else ops.conv3d_pack_weights(mod.weight)
-                pk.bias = mod.bias.detach().float().contiguous() if mod.bias is not None else None
-                pk.cout, pk.cin, pk.k = mod.out_channels, mod.in_channels, k
-                self._conv[id(mod)] = pk
+                if mod.weight.dtype != torch.float32 or not mod.weight.is_contiguous():
+                    raise NotImplementedError("conv weights must be contiguous float32 master weights (use_fp16 / .half() "
+                                              "models are not supported: the fcwdm path keeps its own bf16 operand copies)")
+                forms = [(self._conv, mod.out_channels, mod.in_channels, 0)]
+                if self.want_dgrad and mod.in_channels % 8 == 0:        # the stem conv's input gradient is never needed
+                    forms.append((self._conv_t, mod.in_channels, mod.out_channels, 1))
+                for table, O, I, transposed in forms:
+                    pk = _Packed()
+                    # C_in, C_out <= 64 (the full-resolution layers): kd-fused CTA-pair kernel with resident weights
+                    pk.pair = self.use_pair and ops.conv3d_pair_supported(I, O, k)
+                    n = native.load().fcwdm_conv3d_pair_packed_elems(O, I) if pk.pair else ops.conv3d_packed_elems(O, I, k)
+                    pk.wp = torch.empty(n, dtype=torch.bfloat16, device=device)
+                    pk.cout, pk.cin, pk.k = O, I, k
+                    pk.bias = None
+                    table[id(mod)] = pk
+                    jobs.append([mod.weight.data_ptr(), pk.wp.data_ptr(), O, I, k ** 3, int(pk.pair), transposed, n])
+            self._jobs = torch.tensor(jobs, dtype=torch.int64).to(device)
+            self._jobs_max = max(j[7] for j in jobs)
+            self._layout = layout
+        with ops._on(device) as st:
+            native.call("fcwdm_conv3d_pack_all", ops._ptr(self._jobs), self._jobs.shape[0], self._jobs_max, st)
+        for mod in convs:
+            self._conv[id(mod)].bias = mod.bias.detach().float().contiguous() if mod.bias is not None else None
         # all per-ResBlock timestep projections Linear(SiLU(emb)) (wunet.py:203-206,250) as ONE dense layer:
         # rows of W_cat are the concatenated emb_layers[1] weights; a block reads its column slice of the result
         self._emb_off, ws, bs, off = {}, [], [], 0
@@ -93,7 +117,7 @@ class WavUNetEngine:
         self._device = device
 
     def invalidate(self):
-        """Forget the packed weights (the parameters were updated through raw pointers, e.g. fcwdm.optim.FusedAdamW)."""
+        """The parameters were updated through raw pointers (e.g. fcwdm.optim.FusedAdamW): re-pack on the next call."""
         self._sig = None
 
     def _p32(self, p):

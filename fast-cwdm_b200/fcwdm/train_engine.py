@@ -51,28 +51,10 @@ class WavUNetTrainEngine(WavUNetEngine):
     def _gp(self, p):
         return self._gview[id(p)]
 
+    want_dgrad = True       # WavUNetEngine.prepare then also packs w'[ci][co][tap] = w[co][ci][26-tap] into self._conv_t
+
     def prepare_train(self, device):
         self.prepare(device)
-        if self._tsig == self._sig:
-            return
-        self._conv_t.clear()
-        for mod in self.model.modules():
-            if isinstance(mod, torch.nn.Conv3d):
-                k = mod.kernel_size[0]
-                if mod.in_channels % 8:
-                    continue                                   # the stem conv: its input gradient is never needed
-                wt = ops.conv3d_transpose_flip_weights(mod.weight)
-                pk = _Packed()
-                pk.cin, pk.cout, pk.k = mod.out_channels, mod.in_channels, k
-                pk.pair = self.use_pair and ops.conv3d_pair_supported(pk.cin, pk.cout, k)
-                pk.wp = ops.conv3d_pair_pack_weights(wt) if pk.pair else ops.conv3d_pack_weights(wt)
-                pk.bias = None
-                self._conv_t[id(mod)] = pk
-        self._tsig = self._sig
-
-    def invalidate(self):
-        super().invalidate()
-        self._tsig = None
 
     # ------------------------------------------------------------------ gradient bookkeeping
     def _take(self, t):

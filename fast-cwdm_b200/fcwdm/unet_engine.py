@@ -92,6 +92,15 @@ class UNetEngine(WavUNetEngine):
             width = m.output_blocks[n_in - 1 - j][0].channels
             plan.append((width, width - enc_out_ch[j]))
 
+        def cat_buf(rows, j):
+            # operands narrower than 64 channels are read 64 wide by the TMA box (the extra columns meet zero weights):
+            # inside a concat buffer those columns belong to the neighbour slice / the next row, which must then hold
+            # finite values from the start -> zero-initialise unless every slice is a multiple of 64 channels
+            width, off = plan[j]
+            if off % 64 or (width - off) % 64:
+                return torch.zeros((rows + 1, _ld(width)), dtype=torch.bfloat16, device=dev)[:rows]   # +1: the last row's overhang
+            return self._buf(rows, width, dev)
+
         cats = [None] * n_in
         h, hdims = x_cl, tuple(dims)
         hs_dims = []
@@ -100,7 +109,7 @@ class UNetEngine(WavUNetEngine):
             first = module[0]
             width, off = plan[j]
             if isinstance(first, torch.nn.Conv3d):
-                cat = self._buf(rows_in, width, dev)
+                cat = cat_buf(rows_in, j)
                 view = cat[:, off:off + first.out_channels]
                 h = self._conv3d(first, h, N, hdims, stats_groups=m.num_groups, out=view)
             else:
@@ -112,7 +121,7 @@ class UNetEngine(WavUNetEngine):
                         if layer.updown:
                             fd = 1 if layer.resample_2d else 2
                             od = (hdims[0] // fd, hdims[1] // 2, hdims[2] // 2)
-                        cat = self._buf(N * od[0] * od[1] * od[2], width, dev)
+                        cat = cat_buf(N * od[0] * od[1] * od[2], j)
                         view = cat[:, off:off + layer.out_channels]
                         h, hdims = self._resblock_u(layer, h, emb, N, hdims, out=view)
                     else:

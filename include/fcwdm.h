@@ -255,6 +255,13 @@ int fcwdm_avgpool2_cl(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_
 int fcwdm_upsample2_cl(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t N, int64_t D, int64_t H, int64_t W,
                        int64_t C, int up_depth, void* stream);
 
+/* One-launch re-packing of all conv weights of a model.  jobs: device array of n_jobs records of 8 int64:
+ * {src f32 master weight ptr, dst bf16 packed ptr, O, I, taps, pair, transposed, total}: O/I = output/input channels of
+ * the conv being packed; pair = fcwdm_conv3d_pair_pack_weights layout, else fcwdm_conv3d_pack_weights layout;
+ * transposed = the data-gradient form (fcwdm_conv3d_transpose_flip_weights folded in); total = packed element count.
+ * max_total = the largest `total` (sizes the grid). */
+int fcwdm_conv3d_pack_all(const void* jobs, int64_t n_jobs, int64_t max_total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
