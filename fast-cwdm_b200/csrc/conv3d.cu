@@ -45,6 +45,13 @@ struct ConvArgs {
     double* gn_stats;   // [N][FCWDM_GN_STAT_REPLICAS][gn_groups][2] (pre-zeroed by the caller) or null
     int gn_cpg, gn_groups;
     int a_slots, b_stages;   // runtime split of shared memory between the halo-plane ring and the weight-tile ring
+    // GN_IN variant: the conv input is SiLU(GroupNorm(x)); the raw planes are normalised + activated in shared memory
+    int Cin;                     // real input channels (multiple of 64, <= 256)
+    const double* gi_stats;      // [N][FCWDM_GN_STAT_REPLICAS][gi_groups][2] statistics of x
+    const float* gi_gamma;
+    const float* gi_beta;
+    int gi_groups;
+    float gi_eps;
 };
 
 template <int N_TILE, int TD, int KS>
@@ -58,8 +65,10 @@ struct ConvCfg {
     static constexpr int PLANES = TD + 2 * PAD;
     static constexpr int B_TAP_BYTES = N_TILE * 128;        // one tap's [N_TILE x 64] weight tile
     static constexpr int B_BYTES = KS * B_TAP_BYTES;         // one weight stage = the KS kw-taps of one (kd, kh): one TMA, one barrier round
-    static constexpr int SMEM_BUDGET = 227 * 1024 - 3072;  // 1 KB alignment slack + 1 KB barriers/bias + 1 KB GN statistics
-    static constexpr int MAX_A_SLOTS = 12, MAX_B_STAGES = 16;   // barrier area: 8*(2*12 + 2*16 + 4) + 4 = 484 B < 512
+    // tail after the rings: barriers [0,1024) | bias [1024,1536) | GN statistics [1536,2560) | GN_IN scale/shift [2560,4608)
+    static constexpr int TAIL_BYTES = 4608;
+    static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - TAIL_BYTES;   // 1 KB alignment slack
+    static constexpr int MAX_A_SLOTS = 12, MAX_B_STAGES = 16;   // barrier area: 8*(3*12 + 2*16 + 4) + 4 = 580 B < 1024
     static constexpr int ACC_COLS = TD * N_TILE;
     static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
     static constexpr int TMEM_RAW = ACC_STAGES * ACC_COLS;
@@ -164,8 +173,14 @@ __device__ __forceinline__ void flush_gn_stats(float* wstat, const ConvArgs& arg
     __syncwarp();
 }
 
-template <int N_TILE, int TD, int KS>
-__global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
+__device__ __forceinline__ float c_silu(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return x * fmaf(0.5f, t, 0.5f);
+}
+
+template <int N_TILE, int TD, int KS, bool GN_IN>
+__global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_b,
                                                               const ConvArgs args) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: let the next kernel start its prologue
@@ -183,18 +198,21 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
     const uint32_t empty_b = full_b + 8 * B_STAGES;
     const uint32_t tmem_full = empty_b + 8 * B_STAGES;
     const uint32_t tmem_empty = tmem_full + 8 * Cfg::ACC_STAGES;
-    const uint32_t tmem_slot = tmem_empty + 8 * Cfg::ACC_STAGES;   // 4 B: TMEM base address
+    const uint32_t landed_a = tmem_empty + 8 * Cfg::ACC_STAGES;    // [A_SLOTS] GN_IN: TMA has written the raw plane
+    const uint32_t tmem_slot = landed_a + 8 * A_SLOTS;             // 4 B: TMEM base address
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-    float* wstat = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));   // [4 warps][32 groups][2]
-    float* sbias = reinterpret_cast<float*>(smem_raw + (bars + 512 - smem_u32(smem_raw)));    // [N_TILE] bias + chan_bias of the current tile
+    float* sbias = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));   // [N_TILE] bias + chan_bias of the current tile
+    float* wstat = reinterpret_cast<float*>(smem_raw + (bars + 1536 - smem_u32(smem_raw)));   // [4 warps][32 groups][2]
+    float* sgn = reinterpret_cast<float*>(smem_raw + (bars + 2560 - smem_u32(smem_raw)));     // [2][256] GN_IN scale / shift
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < A_SLOTS; ++i) {
-            mbar_init(full_a + 8 * i, 1);
+            mbar_init(full_a + 8 * i, GN_IN ? 4 : 1);    // GN_IN: the four transform warps hand the plane over
             mbar_init(empty_a + 8 * i, 1);
+            mbar_init(landed_a + 8 * i, 1);
         }
         for (int i = 0; i < B_STAGES; ++i) {
             mbar_init(full_b + 8 * i, 1);
@@ -230,8 +248,9 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
                     for (int p = 0; p < Cfg::PLANES; ++p, ++q) {
                         const uint32_t slot = q % A_SLOTS, ph = (q / A_SLOTS) & 1;
                         mbar_wait(empty_a + 8 * slot, ph ^ 1);
-                        mbar_arrive_expect_tx(full_a + 8 * slot, Cfg::PLANE_BYTES);
-                        tma_load_5d(smem_a + slot * Cfg::SLOT_BYTES, &map_a, full_a + 8 * slot, cb * 64,
+                        const uint32_t land = (GN_IN ? landed_a : full_a) + 8 * slot;
+                        mbar_arrive_expect_tx(land, Cfg::PLANE_BYTES);
+                        tma_load_5d(smem_a + slot * Cfg::SLOT_BYTES, &map_a, land, cb * 64,
                                     tc.w0 - Cfg::PAD, tc.h0 - Cfg::PAD, tc.d0 + p - Cfg::PAD, tc.n);
                     }
                 }
@@ -250,6 +269,86 @@ __global__ void __launch_bounds__(256, 1) conv3d_igemm_kernel(const __grid_const
                         mbar_arrive_expect_tx(full_b + 8 * st, Cfg::B_BYTES);
                         tma_load_3d(smem_b + st * Cfg::B_BYTES, &map_b, full_b + 8 * st, cb * 64, tc.n0, tap);
                     }
+                }
+            }
+        }
+    } else if (GN_IN && warp >= 8) {
+        // ================================ fused GroupNorm + SiLU on the operand path (4 warps) =====================
+        // The raw halo plane landed in shared memory (SWIZZLE_128B, zeros out of range); normalise + activate it in place
+        // and hand it to the MMA issuer.  Out-of-range halo voxels stay ZERO: the convolution pads the ACTIVATED tensor.
+        const int pt = threadIdx.x - 256;                        // 0..127
+        constexpr int CHUNKS = Cfg::HROWS * Cfg::ROWP * 8;        // 16-byte chunks per plane
+        constexpr int PER_THREAD = (CHUNKS + 127) / 128;
+        // physical chunk c = pt + 128 q sits in row c >> 3 at position c & 7; its logical (channel) chunk index
+        // (c & 7) ^ ((c >> 3) & 7) does not depend on q: per-channel scale / shift live in registers per channel block
+        const int jmine = (pt & 7) ^ ((pt >> 3) & 7);
+        int cur_n = -1;
+        uint32_t q = 0;
+        for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+            const TileCoord tc = decode_tile(tile, args, TD, N_TILE);
+            if (tc.n != cur_n) {
+                cur_n = tc.n;
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                const int cpg = args.Cin / args.gi_groups;
+                const double cnt = (double)args.D * args.H * args.W * cpg;
+                for (int c = pt; c < args.Cin; c += 128) {
+                    const int g = c / cpg;
+                    double sum = 0.0, sq = 0.0;
+                    for (int r = 0; r < FCWDM_GN_STAT_REPLICAS; ++r) {
+                        const double* sp = args.gi_stats + (((long long)tc.n * FCWDM_GN_STAT_REPLICAS + r) * args.gi_groups + g) * 2;
+                        sum += sp[0];
+                        sq += sp[1];
+                    }
+                    const double mean = sum / cnt;
+                    double var = sq / cnt - mean * mean;
+                    var = var < 0.0 ? 0.0 : var;
+                    const float rstd = (float)(1.0 / sqrt(var + (double)args.gi_eps));
+                    const float sc0 = rstd * __ldg(args.gi_gamma + c);
+                    sgn[c] = sc0;
+                    sgn[256 + c] = __ldg(args.gi_beta + c) - (float)mean * sc0;
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+            }
+            for (int cb = 0; cb < args.n_cb; ++cb) {
+                float sc[8], sh[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    sc[e] = sgn[cb * 64 + jmine * 8 + e];
+                    sh[e] = sgn[256 + cb * 64 + jmine * 8 + e];
+                }
+                for (int p = 0; p < Cfg::PLANES; ++p, ++q) {
+                    const uint32_t slot = q % A_SLOTS;
+                    const int d = tc.d0 + p - Cfg::PAD;
+                    mbar_wait(landed_a + 8 * slot, (q / A_SLOTS) & 1);
+                    if (d >= 0 && d < args.D) {
+                        uint4* plane = reinterpret_cast<uint4*>(smem_raw + (smem_a + slot * Cfg::SLOT_BYTES - smem_u32(smem_raw)));
+                        uint4 raw[PER_THREAD];
+                        uint32_t valid = 0;
+#pragma unroll
+                        for (int i = 0; i < PER_THREAD; ++i) {
+                            const int c = pt + i * 128;
+                            const int r = c >> 3;
+                            const int hr = r / Cfg::ROWP, wc = r - hr * Cfg::ROWP;
+                            const int h = tc.h0 - Cfg::PAD + hr, w = tc.w0 - Cfg::PAD + wc;
+                            const bool in = (c < CHUNKS) && (h >= 0) && (h < args.H) && (w >= 0) && (w < args.W);
+                            raw[i] = make_uint4(0u, 0u, 0u, 0u);
+                            if (in) {
+                                raw[i] = plane[c];
+                                valid |= 1u << i;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < PER_THREAD; ++i) {
+                            float f[8];
+                            unpack8(raw[i], f);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = c_silu(fmaf(f[e], sc[e], sh[e]));
+                            if (valid & (1u << i)) plane[pt + i * 128] = pack8(f);
+                        }
+                    }
+                    fence_proxy_async();             // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full_a + 8 * slot);
                 }
             }
         }
@@ -458,8 +557,12 @@ static EncodeTiledFn g_encode = nullptr;
 
 template <int N_TILE, int TD, int KS>
 static cudaError_t set_attr() {
-    return cudaFuncSetAttribute(conv3d_igemm_kernel<N_TILE, TD, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                ConvCfg<N_TILE, TD, KS>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv3d_igemm_kernel<N_TILE, TD, KS, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<N_TILE, TD, KS>::SMEM_BYTES);
+    if (e == cudaSuccess && KS == 3 && N_TILE >= 64)
+        e = cudaFuncSetAttribute(conv3d_igemm_kernel<N_TILE, TD, KS, (KS == 3 && N_TILE >= 64)>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<N_TILE, TD, KS>::SMEM_BYTES);
+    return e;
 }
 
 int conv3d_init_device() {
@@ -507,7 +610,15 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, ConvArgs a,
         a.a_slots = as;
         a.b_stages = b;
     }
-    launch_k(conv3d_igemm_kernel<N_TILE, TD, KS>, dim3(grid), dim3(256), Cfg::SMEM_BYTES, st, ma, mb, a);
+    if (a.gi_stats != nullptr) {
+        if constexpr (KS == 3 && N_TILE >= 64) {
+            launch_k(conv3d_igemm_kernel<N_TILE, TD, KS, true>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, st, ma, mb, a);
+        } else {
+            FCWDM_REQUIRE(false, FCWDM_ERR_UNSUPPORTED, "fcwdm_conv3d_gn_fwd: fused input GroupNorm needs a 3x3x3 conv with C_out >= 64");
+        }
+    } else {
+        launch_k(conv3d_igemm_kernel<N_TILE, TD, KS, false>, dim3(grid), dim3(256), Cfg::SMEM_BYTES, st, ma, mb, a);
+    }
     FCWDM_CHECK_LAUNCH("fcwdm_conv3d_fwd");
     return FCWDM_OK;
 }
@@ -539,10 +650,11 @@ extern "C" int fcwdm_conv3d_pack_weights(const float* w, void* wp, int64_t Cout,
     return FCWDM_OK;
 }
 
-extern "C" int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, const float* bias, const float* chan_bias,
-                                int64_t cb_ld, const void* residual, int64_t res_ld, void* y, int64_t y_ld, double* gn_stats,
-                                int64_t gn_groups, int64_t N, int64_t D, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
-                                int ksize, void* stream) {
+static int conv3d_fwd_impl(const void* x, int64_t x_ld, const void* wp, const float* bias, const float* chan_bias,
+                           int64_t cb_ld, const void* residual, int64_t res_ld, void* y, int64_t y_ld, double* gn_stats,
+                           int64_t gn_groups, const double* gn_in_stats, const float* gn_in_gamma, const float* gn_in_beta,
+                           int64_t gn_in_groups, float gn_in_eps, int64_t N, int64_t D, int64_t H, int64_t W, int64_t Cin,
+                           int64_t Cout, int ksize, void* stream) {
     FCWDM_REQUIRE(x && wp && y, FCWDM_ERR_INVALID, "fcwdm_conv3d_fwd: null pointer");
     FCWDM_REQUIRE(N >= 0 && D >= 0 && H >= 0 && W >= 0 && Cin > 0 && Cout > 0, FCWDM_ERR_INVALID,
                   "fcwdm_conv3d_fwd: bad dimension");
@@ -565,6 +677,13 @@ extern "C" int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, con
         const int64_t cpg = Cout / gn_groups;
         FCWDM_REQUIRE(cpg == 1 || cpg == 2 || cpg == 4 || cpg % 8 == 0, FCWDM_ERR_UNSUPPORTED,
                       "fcwdm_conv3d_fwd: fused GroupNorm statistics need channels/group in {1,2,4,8k}");
+    }
+    if (gn_in_stats != nullptr) {
+        FCWDM_REQUIRE(gn_in_gamma && gn_in_beta, FCWDM_ERR_INVALID, "fcwdm_conv3d_gn_fwd: null gamma / beta");
+        FCWDM_REQUIRE(ksize == 3 && Cout >= 64 && Cin % 64 == 0 && Cin <= 256 && gn_in_groups > 0 && Cin % gn_in_groups == 0,
+                      FCWDM_ERR_UNSUPPORTED,
+                      "fcwdm_conv3d_gn_fwd: fused input GroupNorm needs a 3x3x3 conv, C_out >= 64, C_in a multiple of 64 "
+                      "(<= 256) divisible by the group count");
     }
     if (N * D * H * W == 0) return FCWDM_OK;
     if (g_encode == nullptr) {
@@ -608,6 +727,9 @@ extern "C" int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, con
     a.gn_stats = gn_stats;
     a.gn_groups = gn_stats ? (int)gn_groups : 0;
     a.gn_cpg = gn_stats ? (int)(Cout / gn_groups) : 0;
+    a.Cin = (int)Cin;
+    a.gi_stats = gn_in_stats; a.gi_gamma = gn_in_gamma; a.gi_beta = gn_in_beta;
+    a.gi_groups = (int)gn_in_groups; a.gi_eps = gn_in_eps;
     cudaStream_t st = (cudaStream_t)stream;
 
     // tile-shape choice: prefer deep (TD) and wide (N_TILE) tiles for operand reuse, unless that leaves SMs idle
@@ -641,4 +763,22 @@ extern "C" int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, con
     if (nt == 128) return td == 2 ? launch_conv<128, 2, 3>(ma, mb, a, st) : launch_conv<128, 1, 3>(ma, mb, a, st);
     return td == 4 ? launch_conv<64, 4, 3>(ma, mb, a, st)
                    : (td == 2 ? launch_conv<64, 2, 3>(ma, mb, a, st) : launch_conv<64, 1, 3>(ma, mb, a, st));
+}
+
+extern "C" int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, const float* bias, const float* chan_bias,
+                                int64_t cb_ld, const void* residual, int64_t res_ld, void* y, int64_t y_ld, double* gn_stats,
+                                int64_t gn_groups, int64_t N, int64_t D, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                                int ksize, void* stream) {
+    return conv3d_fwd_impl(x, x_ld, wp, bias, chan_bias, cb_ld, residual, res_ld, y, y_ld, gn_stats, gn_groups, nullptr,
+                           nullptr, nullptr, 0, 0.f, N, D, H, W, Cin, Cout, ksize, stream);
+}
+
+extern "C" int fcwdm_conv3d_gn_fwd(const void* x, int64_t x_ld, const void* wp, const float* bias, const float* chan_bias,
+                                   int64_t cb_ld, const void* residual, int64_t res_ld, void* y, int64_t y_ld,
+                                   double* gn_stats, int64_t gn_groups, const double* gn_in_stats, const float* gn_in_gamma,
+                                   const float* gn_in_beta, int64_t gn_in_groups, float gn_in_eps, int64_t N, int64_t D,
+                                   int64_t H, int64_t W, int64_t Cin, int64_t Cout, void* stream) {
+    FCWDM_REQUIRE(gn_in_stats != nullptr, FCWDM_ERR_INVALID, "fcwdm_conv3d_gn_fwd: null input statistics");
+    return conv3d_fwd_impl(x, x_ld, wp, bias, chan_bias, cb_ld, residual, res_ld, y, y_ld, gn_stats, gn_groups, gn_in_stats,
+                           gn_in_gamma, gn_in_beta, gn_in_groups, gn_in_eps, N, D, H, W, Cin, Cout, 3, stream);
 }

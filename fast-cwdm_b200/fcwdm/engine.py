@@ -45,6 +45,7 @@ class WavUNetEngine:
         self.fuse_stats_rows = int(os.environ.get("FCWDM_FUSED_STATS_ROWS", "20000"))   # <= 28x28x20 voxels per batch
         self.use_pair = os.environ.get("FCWDM_NO_PAIR", "0") != "1"
         self.fuse_gn_in = os.environ.get("FCWDM_NO_FUSED_GN_IN", "0") != "1"
+        self.fuse_gn_in_general = os.environ.get("FCWDM_NO_FUSED_GN_IN_GENERAL", "0") != "1"   # single-CTA kernel too
 
     # ------------------------------------------------------------------ weights
     def _signature(self):
@@ -158,9 +159,9 @@ class WavUNetEngine:
                                residual=residual, gn_stats=stats, gn_groups=stats_groups if stats is not None else 0,
                                gn_in=gn_in)
         else:
-            assert gn_in is None
             ops.conv3d_cl(x, pk.wp, pk.bias, y, (N,) + tuple(dims), pk.cin, pk.cout, pk.k, chan_bias=chan_bias,
-                          residual=residual, gn_stats=stats, gn_groups=stats_groups if stats is not None else 0)
+                          residual=residual, gn_stats=stats, gn_groups=stats_groups if stats is not None else 0,
+                          gn_in=gn_in)
         return y
 
     def _stats_slot(self, N, G, device):
@@ -193,7 +194,8 @@ class WavUNetEngine:
         operand producers (no GroupNorm-apply pass, no intermediate tensor); otherwise apply, then convolve."""
         pk = self._conv[id(mod)]
         S = dims[0] * dims[1] * dims[2]
-        if pk.pair and self.fuse_gn_in and gn.num_channels == pk.cin and pk.cin % gn.num_groups == 0:
+        fusable = pk.pair or (self.fuse_gn_in_general and pk.k == 3 and pk.cout >= 64 and pk.cin % 64 == 0 and pk.cin <= 256)
+        if fusable and self.fuse_gn_in and gn.num_channels == pk.cin and pk.cin % gn.num_groups == 0:
             stats, have = self._take_stats(gn, x, N)
             if not have:
                 ops.groupnorm_stats(x, stats, N, S, pk.cin, gn.num_groups)

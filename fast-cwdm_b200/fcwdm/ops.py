@@ -230,10 +230,19 @@ def conv3d_pack_weights(w):
     return wp
 
 
-def conv3d_cl(x, wp, bias, y, dims, cin, cout, k, chan_bias=None, residual=None, gn_stats=None, gn_groups=0):
+def conv3d_cl(x, wp, bias, y, dims, cin, cout, k, chan_bias=None, residual=None, gn_stats=None, gn_groups=0, gn_in=None):
     """x, y, residual: cl bf16 buffers (voxels, ld).  dims = (N, D, H, W).  gn_stats: optional PRE-ZEROED
-    (N, GN_STAT_REPLICAS, gn_groups, 2) float64 buffer that receives the GroupNorm statistics of y."""
+    (N, GN_STAT_REPLICAS, gn_groups, 2) float64 buffer that receives the GroupNorm statistics of y.
+    gn_in = (stats, gamma, beta, groups, eps): convolve SiLU(GroupNorm(x)), normalised in the kernel's operand path."""
     N, D, H, W = dims
+    if gn_in is not None:
+        assert k == 3
+        with _on(x.device) as st:
+            native.call("fcwdm_conv3d_gn_fwd", _ptr(x), x.stride(0), _ptr(wp), _ptr(bias), _ptr(chan_bias),
+                        chan_bias.stride(0) if chan_bias is not None else 0, _ptr(residual),
+                        residual.stride(0) if residual is not None else 0, _ptr(y), y.stride(0), _ptr(gn_stats), gn_groups,
+                        _ptr(gn_in[0]), _ptr(gn_in[1]), _ptr(gn_in[2]), gn_in[3], float(gn_in[4]), N, D, H, W, cin, cout, st)
+        return
     with _on(x.device) as st:
         native.call("fcwdm_conv3d_fwd", _ptr(x), x.stride(0), _ptr(wp), _ptr(bias), _ptr(chan_bias),
                     chan_bias.stride(0) if chan_bias is not None else 0, _ptr(residual),

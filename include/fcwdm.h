@@ -166,12 +166,21 @@ int fcwdm_linear(const float* x, const float* W, const float* b, float* y, int64
  *   double [N][FCWDM_GN_STAT_REPLICAS][gn_groups][2] that fcwdm_groupnorm_apply consumes directly, so the
  *   next GroupNorm needs no statistics pass over y.
  * ---------------------------------------------------------------------------------------------------- */
+/* fcwdm_conv3d_gn_fwd: the same 3x3x3 convolution of SiLU(GroupNorm(x)) with the normalisation + activation applied to
+ * the halo planes in shared memory by four extra warps (x is the RAW tensor; gn_in_stats = its statistics in the
+ * fcwdm_groupnorm_stats layout): the GroupNorm-apply pass and its intermediate tensor (nn.py:17-19 + nn.SiLU,
+ * wunet.py:186-187,210-211; unet.py:225-229,249-256) disappear.  C_in a multiple of 64 (<= 256), C_out >= 64. */
 int64_t fcwdm_conv3d_packed_elems(int64_t Cout, int64_t Cin, int ksize);
 int fcwdm_conv3d_pack_weights(const float* w, void* wp, int64_t Cout, int64_t Cin, int ksize, void* stream);
 int fcwdm_conv3d_fwd(const void* x, int64_t x_ld, const void* wp, const float* bias, const float* chan_bias,
                      int64_t cb_ld, const void* residual, int64_t res_ld, void* y, int64_t y_ld, double* gn_stats,
                      int64_t gn_groups, int64_t N, int64_t D, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
                      int ksize, void* stream);
+int fcwdm_conv3d_gn_fwd(const void* x, int64_t x_ld, const void* wp, const float* bias, const float* chan_bias,
+                        int64_t cb_ld, const void* residual, int64_t res_ld, void* y, int64_t y_ld, double* gn_stats,
+                        int64_t gn_groups, const double* gn_in_stats, const float* gn_in_gamma, const float* gn_in_beta,
+                        int64_t gn_in_groups, float gn_in_eps, int64_t N, int64_t D, int64_t H, int64_t W, int64_t Cin,
+                        int64_t Cout, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * K5b: the same 3x3x3 convolution for C_in <= 64 and C_out <= 64 (the full-resolution layers) as a kd-fused,

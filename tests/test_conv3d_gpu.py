@@ -194,3 +194,44 @@ def test_conv3d_pair_fused_input_groupnorm(case):
     ref = F.conv3d(a, w, bias, padding=1)
     err = float((got - ref).abs().max())
     assert err <= 2e-2 * float(ref.abs().max()) + 2e-3, err
+
+
+GN_IN_CASES = [
+    # N, D, H, W, cin, cout, groups
+    (1, 4, 16, 8, 128, 128, 32),     # two channel blocks, one tile per plane pair
+    (2, 5, 18, 10, 64, 128, 32),     # batch 2 (per-sample statistics), ragged tiles
+    (1, 3, 7, 5, 256, 256, 32),      # bottleneck shape family, four channel blocks
+    (1, 6, 20, 12, 192, 64, 32),     # 6 channels per group (plain U-Net concat width), N_TILE = 64
+    (1, 8, 16, 16, 128, 64, 8),
+]
+
+
+@pytest.mark.parametrize("case", GN_IN_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv3d_fused_input_groupnorm(case):
+    """fcwdm_conv3d_gn_fwd == conv(SiLU(GroupNorm(x))) + bias + per-sample channel bias + residual: the halo planes are
+    normalised in shared memory by the kernel; zero padding applies to the ACTIVATED tensor."""
+    from fcwdm import ops
+    from gpu_util import bf16_round, from_cl, to_cl
+    N, D, H, W, cin, cout, G = case
+    g = torch.Generator().manual_seed(7)
+    x = bf16_round(torch.randn(N, cin, D, H, W, generator=g) * 1.3 + 0.4).cuda()
+    w = bf16_round(torch.randn(cout, cin, 3, 3, 3, generator=g) / np.sqrt(cin * 27)).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    cb = torch.randn(N, cout, generator=g).cuda()
+    res = bf16_round(torch.randn(N, cout, D, H, W, generator=g)).cuda()
+    gamma = (torch.randn(cin, generator=g) * 0.3 + 1.0).cuda()
+    beta = (torch.randn(cin, generator=g) * 0.2).cuda()
+    xc = to_cl(x)
+    S = D * H * W
+    stats = torch.empty((N, ops.GN_STAT_REPLICAS, G, 2), dtype=torch.float64, device="cuda")
+    ops.groupnorm_stats(xc, stats, N, S, cin, G)
+    yc = torch.zeros((N * S, (cout + 63) // 64 * 64), dtype=torch.bfloat16, device="cuda")
+    ops.conv3d_cl(xc, ops.conv3d_pack_weights(w), bias, yc, (N, D, H, W), cin, cout, 3, chan_bias=cb, residual=to_cl(res),
+                  gn_in=(stats, gamma, beta, G, 1e-5))
+    torch.cuda.synchronize()
+    got = from_cl(yc, (N, cout, D, H, W))
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    a = bf16_round(F.silu(F.group_norm(x, G, gamma, beta, 1e-5)))       # the kernel feeds bf16 operands to the MMA
+    ref = F.conv3d(a, w, bias, padding=1) + cb[:, :, None, None, None] + res
+    check(got, ref)
