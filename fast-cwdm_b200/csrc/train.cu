@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kTrThreads) gn_bwd_reduce_kernel(const __nv_bf
     const int n = blockIdx.y;
     const int cpg = C / G;
     const double cnt = (double)S * (double)cpg;
-    for (int c = threadIdx.x; c < C; c += kTrThreads) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float rstd, mean;
         gn_channel_norm(stats, n, c / cpg, G, cnt, eps, rstd, mean);
         coef[c] = rstd;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kTrThreads) gn_bwd_reduce_kernel(const __nv_bf
     const int C8 = C >> 3;
     const int chunk = threadIdx.x % C8;
     const int lane = threadIdx.x / C8;
-    const int vpb = kTrThreads / C8;
+    const int vpb = blockDim.x / C8;
     float xs[8], xh[8], gm[8], bt[8], a[8], b[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kTrThreads) gn_bwd_reduce_kernel(const __nv_bf
     }
     __syncthreads();
     double* dst = sums + (((int64_t)n * kTrReplicas + (blockIdx.x % kTrReplicas)) * C) * 2;
-    for (int i = threadIdx.x; i < 2 * C; i += kTrThreads) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
         const int comp = i / C, c = i % C;
         const float* p = part + (comp * 8 + (c & 7)) * kTrThreads + (c >> 3);
         float acc = 0.f;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kTrThreads) gn_bwd_apply_kernel(const __nv_bfl
     const double cnt = (double)S * (double)cpg;
     float* ga = sm + 6 * C;
     float* gb = sm + 7 * C;
-    for (int c = threadIdx.x; c < C; c += kTrThreads) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float rstd, mean;
         gn_channel_norm(stats, n, c / cpg, G, cnt, eps, rstd, mean);
         double A = 0.0, B = 0.0;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kTrThreads) gn_bwd_apply_kernel(const __nv_bfl
         }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += kTrThreads) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g0 = (c / cpg) * cpg;
         float s1 = 0.f, s2 = 0.f;
         for (int e = 0; e < cpg; ++e) {
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kTrThreads) gn_bwd_apply_kernel(const __nv_bfl
     const int C8 = C >> 3;
     const int chunk = threadIdx.x % C8;
     const int lane = threadIdx.x / C8;
-    const int vpb = kTrThreads / C8;
+    const int vpb = blockDim.x / C8;
     float xs[8], xh[8], gm[8], bt[8], k1[8], k2[8], k3[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kTrThreads) colsum_cl_kernel(const __nv_bfloat
     const int C8 = C >> 3;
     const int chunk = threadIdx.x % C8;
     const int lane = threadIdx.x / C8;
-    const int vpb = kTrThreads / C8;
+    const int vpb = blockDim.x / C8;
     float a[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[j] = 0.f;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kTrThreads) colsum_cl_kernel(const __nv_bfloat
 #pragma unroll
     for (int j = 0; j < 8; ++j) sm[j * kTrThreads + threadIdx.x] = a[j];
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += kTrThreads) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float* p = sm + (c & 7) * kTrThreads + (c >> 3);
         float acc = 0.f;
         for (int l = 0; l < vpb; ++l) acc += p[l * C8];
@@ -530,8 +530,8 @@ static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) 
 static int gn_bwd_check(const char* fn, int64_t N, int64_t S, int64_t C, int64_t G) {
     FCWDM_REQUIRE(N >= 0 && S >= 0 && C > 0 && G > 0 && N <= 65535, FCWDM_ERR_INVALID, "%s: bad dimension", fn);
     FCWDM_REQUIRE(C % G == 0, FCWDM_ERR_INVALID, "%s: C (%lld) not divisible by G (%lld)", fn, (long long)C, (long long)G);
-    FCWDM_REQUIRE(C % 8 == 0 && (kTrThreads % (C / 8)) == 0 && C <= 1024, FCWDM_ERR_UNSUPPORTED,
-                  "%s: C must be 8 * a divisor of %d, at most 1024 (got %lld)", fn, kTrThreads, (long long)C);
+    FCWDM_REQUIRE(C % 8 == 0 && C <= 1024, FCWDM_ERR_UNSUPPORTED, "%s: C must be a multiple of 8, at most 1024 (got %lld)",
+                  fn, (long long)C);
     return FCWDM_OK;
 }
 
@@ -565,17 +565,18 @@ extern "C" int fcwdm_groupnorm_bwd(const void* x, int64_t x_ld, const void* dy, 
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * N * C * kTrReplicas, st);
     FCWDM_REQUIRE(e == cudaSuccess, FCWDM_ERR_CUDA, "fcwdm_groupnorm_bwd: memset failed (%s)", cudaGetErrorString(e));
     const dim3 grid = slab_grid(N, S, C, 4);
+    const dim3 blk((unsigned)((kTrThreads / (C / 8)) * (C / 8)));      // 256, or e.g. 240 for C = 192 / 384
     const size_t sm1 = (16 * kTrThreads + 4 * C) * sizeof(float), sm2 = 8 * C * sizeof(float);
     const __nv_bfloat16 *xp = (const __nv_bfloat16*)x, *dp = (const __nv_bfloat16*)dy, *ap = (const __nv_bfloat16*)acc;
     if (silu) {
-        launch_k(gn_bwd_reduce_kernel<true>, grid, dim3(kTrThreads), sm1, st, xp, x_ld, dp, dy_ld, stats, gamma, beta, sums,
+        launch_k(gn_bwd_reduce_kernel<true>, grid, blk, sm1, st, xp, x_ld, dp, dy_ld, stats, gamma, beta, sums,
                  S, (int)C, (int)G, eps);
-        launch_k(gn_bwd_apply_kernel<true>, grid, dim3(kTrThreads), sm2, st, xp, x_ld, dp, dy_ld, stats, gamma, beta,
+        launch_k(gn_bwd_apply_kernel<true>, grid, blk, sm2, st, xp, x_ld, dp, dy_ld, stats, gamma, beta,
                  (const double*)sums, ap, acc_ld, (__nv_bfloat16*)dx, dx_ld, dgamma, dbeta, S, (int)C, (int)G, eps);
     } else {
-        launch_k(gn_bwd_reduce_kernel<false>, grid, dim3(kTrThreads), sm1, st, xp, x_ld, dp, dy_ld, stats, gamma, beta, sums,
+        launch_k(gn_bwd_reduce_kernel<false>, grid, blk, sm1, st, xp, x_ld, dp, dy_ld, stats, gamma, beta, sums,
                  S, (int)C, (int)G, eps);
-        launch_k(gn_bwd_apply_kernel<false>, grid, dim3(kTrThreads), sm2, st, xp, x_ld, dp, dy_ld, stats, gamma, beta,
+        launch_k(gn_bwd_apply_kernel<false>, grid, blk, sm2, st, xp, x_ld, dp, dy_ld, stats, gamma, beta,
                  (const double*)sums, ap, acc_ld, (__nv_bfloat16*)dx, dx_ld, dgamma, dbeta, S, (int)C, (int)G, eps);
     }
     FCWDM_CHECK_LAUNCH("fcwdm_groupnorm_bwd");
@@ -586,11 +587,10 @@ extern "C" int fcwdm_colsum_cl(const void* x, int64_t ld, float* out_sample, int
                                int64_t S, int64_t C, void* stream) {
     FCWDM_REQUIRE(x && (out_sample || out_total), FCWDM_ERR_INVALID, "fcwdm_colsum_cl: null pointer");
     FCWDM_REQUIRE(N >= 0 && S >= 0 && C > 0 && N <= 65535, FCWDM_ERR_INVALID, "fcwdm_colsum_cl: bad dimension");
-    FCWDM_REQUIRE(C % 8 == 0 && (kTrThreads % (C / 8)) == 0 && C <= 2048 && ld >= C && ld % 8 == 0 && al16(x),
-                  FCWDM_ERR_UNSUPPORTED, "fcwdm_colsum_cl: C must be 8 * a divisor of %d, ld >= C, 16-byte aligned",
-                  kTrThreads);
+    FCWDM_REQUIRE(C % 8 == 0 && C <= 2048 && ld >= C && ld % 8 == 0 && al16(x), FCWDM_ERR_UNSUPPORTED,
+                  "fcwdm_colsum_cl: C must be a multiple of 8 (<= 2048), ld >= C, 16-byte aligned");
     if (N * S == 0) return FCWDM_OK;
-    launch_k(colsum_cl_kernel, slab_grid(N, S, C, 8), dim3(kTrThreads), 8 * kTrThreads * sizeof(float),
+    launch_k(colsum_cl_kernel, slab_grid(N, S, C, 8), dim3((unsigned)((kTrThreads / (C / 8)) * (C / 8))), 8 * kTrThreads * sizeof(float),
              (cudaStream_t)stream, (const __nv_bfloat16*)x, ld, out_sample, os_ld, out_total, S, (int)C);
     FCWDM_CHECK_LAUNCH("fcwdm_colsum_cl");
     return FCWDM_OK;

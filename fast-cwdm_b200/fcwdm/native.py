@@ -64,6 +64,8 @@ PROTOTYPES = {
     "fcwdm_conv3d_pack_all": (_c_int, [_c_p, _c_i64, _c_i64, _c_p]),
     "fcwdm_conv3d_gn_fwd": (_c_int, [_c_p, _c_i64, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64,
                                      _c_p, _c_p, _c_p, _c_i64, _c_f] + [_c_i64] * 6 + [_c_p]),
+    "fcwdm_avgpool2_cl_bwd": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64] + [_c_i64] * 5 + [_c_int, _c_p]),
+    "fcwdm_upsample2_cl_bwd": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64] + [_c_i64] * 5 + [_c_int, _c_p]),
 }
 
 FCWDM_F32, FCWDM_BF16 = 0, 1

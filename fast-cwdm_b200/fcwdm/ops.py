@@ -441,3 +441,19 @@ def upsample2_cl(x, dims, C, y, up_depth=True):
     N, D, H, W = dims
     with _on(x.device) as st:
         native.call("fcwdm_upsample2_cl", _ptr(x), x.stride(0), _ptr(y), y.stride(0), N, D, H, W, C, 1 if up_depth else 0, st)
+
+
+def avgpool2_cl_bwd(dy, dims, C, dx, acc=None, pool_depth=True):
+    """Adjoint of avgpool2_cl; dims = (N, D, H, W) of dy (the pooled tensor)."""
+    N, D, H, W = dims
+    with _on(dy.device) as st:
+        native.call("fcwdm_avgpool2_cl_bwd", _ptr(dy), dy.stride(0), _ptr(acc), acc.stride(0) if acc is not None else 0,
+                    _ptr(dx), dx.stride(0), N, D, H, W, C, 1 if pool_depth else 0, st)
+
+
+def upsample2_cl_bwd(dy, dims, C, dx, acc=None, up_depth=True):
+    """Adjoint of upsample2_cl; dims = (N, D, H, W) of dy (the up-sampled tensor)."""
+    N, D, H, W = dims
+    with _on(dy.device) as st:
+        native.call("fcwdm_upsample2_cl_bwd", _ptr(dy), dy.stride(0), _ptr(acc), acc.stride(0) if acc is not None else 0,
+                    _ptr(dx), dx.stride(0), N, D, H, W, C, 1 if up_depth else 0, st)

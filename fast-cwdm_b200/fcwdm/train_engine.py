@@ -32,6 +32,7 @@ class WavUNetTrainEngine(WavUNetEngine):
         self._tape = []
         self._grads = {}
         self._keep = []
+        self._uses = {}
         self.grad_ready_hook = None      # callable(lo, hi): flat-gradient range [lo, hi) is final (fcwdm.ddp)
         self.grad_sync = None            # fcwdm.ddp.GradSync: bucketed all-reduce overlapped with the backward
 
@@ -87,13 +88,14 @@ class WavUNetTrainEngine(WavUNetEngine):
         return torch.zeros((rows, _ld(C)), dtype=torch.bfloat16, device=device)
 
     # ------------------------------------------------------------------ taped building blocks
-    def _conv3d_t(self, mod, x, N, dims, emb=None, residual=None, out_ld=None, stats_groups=0, need_dx=True):
+    def _conv3d_t(self, mod, x, N, dims, emb=None, residual=None, out_ld=None, stats_groups=0, need_dx=True, out=None):
         """emb = (d_emb_all, off, n, emb_slice): the timestep-embedding add fused in the conv epilogue."""
         pk = self._conv[id(mod)]
         rows = N * dims[0] * dims[1] * dims[2]
-        y = self._conv3d(mod, x, N, dims, chan_bias=emb[3] if emb else None, residual=residual, out_ld=out_ld,
-                         stats_groups=stats_groups)
+        y = WavUNetEngine._conv3d(self, mod, x, N, dims, chan_bias=emb[3] if emb else None, residual=residual,
+                                  out_ld=out_ld, stats_groups=stats_groups, out=out)
         self._keep.append((x, y, residual))
+        self._count(mod.weight, mod.bias)
         dims4 = (N,) + tuple(dims)
 
         def bwd():
@@ -132,6 +134,7 @@ class WavUNetTrainEngine(WavUNetEngine):
         gamma, beta = self._p32(gn.weight), self._p32(gn.bias)
         ops.groupnorm_silu(x, y, stats, gamma, beta, N, S, C, gn.num_groups, gn.eps, silu, have_stats=have)
         self._keep.append((x, y))
+        self._count(gn.weight, gn.bias)
 
         def bwd():
             dy = self._take(y)
@@ -149,6 +152,12 @@ class WavUNetTrainEngine(WavUNetEngine):
     def _gn_silu_conv(self, gn, x, mod, N, dims, **kw):       # training: GroupNorm output materialised (wgrad operand)
         S = dims[0] * dims[1] * dims[2]
         return self._conv3d_t(mod, self._gn_silu_t(gn, x, N, S), N, dims, **kw)
+
+    def _count(self, *params):
+        """One more tape entry contributes to these parameters (weight-tied blocks are taped twice)."""
+        for p in params:
+            if p is not None:
+                self._uses[id(p)] = self._uses.get(id(p), 0) + 1
 
     def _param_done(self, *params):
         if self.grad_ready_hook is not None:
@@ -259,6 +268,43 @@ class WavUNetTrainEngine(WavUNetEngine):
                                  stats_groups=self.model.num_groups)
         return out, skip_out, dims
 
+    def _time_path_t(self, t, N, dev):
+        """Timestep path (wunet.py:472-475,736 / unet.py:777; ResBlock emb_layers) with pre-activations kept and the
+        backward taped.  Returns (emb_all, d_emb_all): all per-block projections and their gradient accumulator."""
+        m = self.model
+        l0, l2 = m.time_embed[0], m.time_embed[2]
+        te = torch.empty((N, m.model_channels), dtype=torch.float32, device=dev)
+        ops.timestep_embedding(t, te, m.model_channels)
+        z1 = torch.empty((N, l0.out_features), dtype=torch.float32, device=dev)
+        ops.linear(te, self._p32(l0.weight), self._p32(l0.bias), z1, act_in=0, act_out=0)
+        e2 = torch.empty((N, l2.out_features), dtype=torch.float32, device=dev)
+        ops.linear(z1, self._p32(l2.weight), self._p32(l2.bias), e2, act_in=1, act_out=0)
+        emb_all = WavUNetEngine._emb_all(self, e2)
+        d_emb_all = torch.zeros_like(emb_all)
+        blocks, seen = [], set()
+        for mod in m.modules():
+            if hasattr(mod, "emb_layers") and hasattr(mod, "in_layers") and id(mod) not in seen:
+                seen.add(id(mod))
+                blocks.append(mod)
+                self._count(mod.emb_layers[1].weight, mod.emb_layers[1].bias)
+        self._count(l2.weight, l2.bias, l0.weight, l0.bias)
+
+        def emb_bwd():
+            for mod in blocks:
+                lin = mod.emb_layers[1]
+                off, n = self._emb_off[id(mod)]
+                ops.linear_bwd(e2, None, d_emb_all[:, off:off + n], dW=self._gp(lin.weight), db=self._gp(lin.bias), act_in=1)
+                self._param_done(lin.weight, lin.bias)
+            d_e2 = torch.empty_like(e2)
+            ops.linear_bwd(e2, self._emb_w, d_emb_all, dx=d_e2, act_in=1)
+            d_z1 = torch.empty_like(z1)
+            ops.linear_bwd(z1, self._p32(l2.weight), d_e2, dx=d_z1, dW=self._gp(l2.weight), db=self._gp(l2.bias), act_in=1)
+            ops.linear_bwd(te, None, d_z1, dW=self._gp(l0.weight), db=self._gp(l0.bias), act_in=0)
+            self._param_done(l2.weight, l2.bias, l0.weight, l0.bias)
+
+        self._tape.append(emb_bwd)
+        return emb_all, d_emb_all
+
     # ------------------------------------------------------------------ whole network
     def forward_train(self, x, timesteps):
         """Planar fp32 (N, C, D, H, W) -> (N, out_channels, D, H, W), recording the backward tape."""
@@ -280,7 +326,7 @@ class WavUNetTrainEngine(WavUNetEngine):
         with torch.cuda.device(dev):
             self.prepare_train(dev)
             self.flat_grad(dev)
-            self._tape, self._grads, self._keep = [], {}, []
+            self._tape, self._grads, self._keep, self._uses = [], {}, [], {}
             self._stats.clear()
             self._arena = torch.zeros(1 << 18, dtype=torch.float64, device=dev)
             self._arena_pos = 0
@@ -289,35 +335,7 @@ class WavUNetTrainEngine(WavUNetEngine):
             ops.planar_to_cl(x.detach().float(), x_cl, C)
             t = timesteps.to(torch.int64).contiguous()
 
-            # ---- timestep path (wunet.py:472-475,736; ResBlock emb_layers :203-206), pre-activations kept
-            l0, l2 = m.time_embed[0], m.time_embed[2]
-            te = torch.empty((N, m.model_channels), dtype=torch.float32, device=dev)
-            ops.timestep_embedding(t, te, m.model_channels)
-            z1 = torch.empty((N, l0.out_features), dtype=torch.float32, device=dev)
-            ops.linear(te, self._p32(l0.weight), self._p32(l0.bias), z1, act_in=0, act_out=0)
-            e2 = torch.empty((N, l2.out_features), dtype=torch.float32, device=dev)
-            ops.linear(z1, self._p32(l2.weight), self._p32(l2.bias), e2, act_in=1, act_out=0)
-            emb_all = self._emb_all(e2)
-            d_emb_all = torch.zeros_like(emb_all)
-
-            def emb_bwd():
-                seen = set()
-                for mod in m.modules():
-                    if isinstance(mod, ResBlock) and id(mod) not in seen:
-                        seen.add(id(mod))
-                        lin = mod.emb_layers[1]
-                        off, n = self._emb_off[id(mod)]
-                        ops.linear_bwd(e2, None, d_emb_all[:, off:off + n], dW=self._gp(lin.weight), db=self._gp(lin.bias),
-                                       act_in=1)
-                        self._param_done(lin.weight, lin.bias)
-                d_e2 = torch.empty_like(e2)
-                ops.linear_bwd(e2, self._emb_w, d_emb_all, dx=d_e2, act_in=1)
-                d_z1 = torch.empty_like(z1)
-                ops.linear_bwd(z1, self._p32(l2.weight), d_e2, dx=d_z1, dW=self._gp(l2.weight), db=self._gp(l2.bias), act_in=1)
-                ops.linear_bwd(te, None, d_z1, dW=self._gp(l0.weight), db=self._gp(l0.bias), act_in=0)
-                self._param_done(l2.weight, l2.bias, l0.weight, l0.bias)
-
-            self._tape.append(emb_bwd)
+            emb_all, d_emb_all = self._time_path_t(t, N, dev)
 
             # ---- U-Net (mirrors WavUNetEngine.forward_cl / reference wunet.py:734-795)
             hs = []
@@ -376,7 +394,7 @@ class WavUNetTrainEngine(WavUNetEngine):
         with torch.cuda.device(dev):
             self._gflat.zero_()
             if self.grad_ready_hook is not None:
-                self._uses_left = dict(self._use_count())
+                self._uses_left = dict(self._uses)
             if self.grad_sync is not None:
                 self.grad_sync.begin()
             dy = torch.zeros((N * D * H * W, _ld(m.out_channels)), dtype=torch.bfloat16, device=dev)
@@ -389,33 +407,6 @@ class WavUNetTrainEngine(WavUNetEngine):
             self._tape, self._grads, self._keep, self._out_cl = [], {}, [], None
             self._stats.clear()
         return self._gflat
-
-    def _use_count(self):
-        """How many tape entries contribute to each parameter (weight-tied blocks run twice)."""
-        from guided_diffusion.wunet import ResBlock
-        cnt = {id(p): 0 for p in self.model.parameters()}
-        m = self.model
-
-        def visit_block(blk):
-            for p in blk.parameters():
-                cnt[id(p)] += 1
-
-        for module in m.input_blocks:
-            for layer in module:
-                visit_block(layer)
-        for layer in m.middle_block:
-            visit_block(layer)
-        for module in m.output_blocks:
-            for layer in module:
-                visit_block(layer)
-        for module in m.out_res:
-            for layer in module:
-                visit_block(layer)
-        for p in m.out.parameters():
-            cnt[id(p)] += 1
-        for p in m.time_embed.parameters():
-            cnt[id(p)] += 1
-        return cnt
 
     def grad_views(self):
         """Per-parameter views of a COPY of the flat gradient (autograd may adopt them as .grad and later accumulate
@@ -445,3 +436,112 @@ class WavUNetFunction(torch.autograd.Function):
         eng = ctx.engine
         eng.backward(dout)
         return (None, None, None) + tuple(eng.grad_views())
+
+
+class UNetTrainEngine(WavUNetTrainEngine):
+    """Training execution of the plain UNetModel (run.sh's use_freq=False model, the one scripts/train.py actually
+    trains): UNetEngine's launch plan with every primitive taped.  The skip concatenations stay zero-copy in the
+    backward as well: the gradient of a concat buffer is split into two column-slice views."""
+
+    def __init__(self, model):
+        super().__init__(model)
+        self._emb_map = {}
+        self._x_in = None
+        self._d_emb_all = None
+
+    # UNetEngine's forward plan, with this class's taped primitives underneath
+    from .unet_engine import UNetEngine as _U
+    forward_cl = _U.forward_cl
+    _resblock_u = _U._resblock_u
+    del _U
+
+    def time_embedding(self, t):
+        return t                                            # the taped time path runs in _emb_all
+
+    def _emb_all(self, t):
+        emb_all, self._d_emb_all = self._time_path_t(t, t.shape[0], t.device)
+        return emb_all
+
+    def _emb_out(self, blk, emb_all):
+        off, n = self._emb_off[id(blk)]
+        v = emb_all[:, off:off + n]
+        self._emb_map[id(v)] = (self._d_emb_all, off, n, v)     # holding v keeps its id unique for this forward
+        return v
+
+    def _conv3d(self, mod, x, N, dims, chan_bias=None, residual=None, out_ld=None, stats_groups=0, gn_in=None, out=None):
+        emb = self._emb_map[id(chan_bias)] if chan_bias is not None else None
+        return self._conv3d_t(mod, x, N, dims, emb=emb, residual=residual, out_ld=out_ld, stats_groups=stats_groups,
+                              need_dx=x is not self._x_in, out=out)
+
+    def _gn_silu(self, gn, x, N, S, silu=True):
+        return self._gn_silu_t(gn, x, N, S, silu)
+
+    def _gn_silu_conv(self, gn, x, mod, N, dims, **kw):
+        S = dims[0] * dims[1] * dims[2]
+        return self._conv3d(mod, self._gn_silu(gn, x, N, S), N, dims, **kw)
+
+    def _resample(self, x, N, dims, C, up, depth):
+        fd = 2 if depth else 1
+        d2 = (dims[0] * fd, dims[1] * 2, dims[2] * 2) if up else (dims[0] // fd, dims[1] // 2, dims[2] // 2)
+        y = self._buf(N * d2[0] * d2[1] * d2[2], C, x.device)
+        if up:
+            ops.upsample2_cl(x, (N,) + tuple(dims), C, y, up_depth=depth)
+        else:
+            ops.avgpool2_cl(x, (N,) + tuple(dims), C, y, pool_depth=depth)
+        self._keep.append((x, y))
+        rows_x = N * dims[0] * dims[1] * dims[2]
+
+        def bwd():
+            dy = self._take(y)
+            if dy is None:
+                return
+            dx = self._buf(rows_x, C, x.device)
+            if up:
+                ops.upsample2_cl_bwd(dy, (N,) + d2, C, dx, acc=self._partial(x), up_depth=depth)
+            else:
+                ops.avgpool2_cl_bwd(dy, (N,) + d2, C, dx, acc=self._partial(x), pool_depth=depth)
+            self._set(x, dx)
+
+        self._tape.append(bwd)
+        return y, d2
+
+    def _on_concat(self, cat, left, right, plan_j, rows):
+        width, off = plan_j
+        self._keep.append((cat, left, right))
+
+        def bwd():
+            dcat = self._take(cat)
+            if dcat is None:
+                return
+            self._pass(left, dcat[:, :off], rows, off)
+            self._pass(right, dcat[:, off:width], rows, width - off)
+
+        self._tape.append(bwd)
+
+    def forward_train(self, x, timesteps):
+        m = self.model
+        if not x.is_cuda:
+            raise FcwdmError("UNetModel.forward: input is on the CPU; the fcwdm denoiser has no CPU path")
+        if x.dim() != 5 or x.shape[1] != m.in_channels:
+            raise ValueError(f"expected input of shape (N, {m.in_channels}, D, H, W), got {tuple(x.shape)}")
+        if timesteps.is_floating_point():
+            raise NotImplementedError("fractional timesteps (rescale_timesteps=True) are not implemented")
+        for mod in m.modules():
+            if getattr(mod, "dropout", 0) and hasattr(mod, "in_layers"):
+                raise NotImplementedError("dropout > 0 in training is not implemented (run.sh ships dropout=0)")
+        N, C, D, H, W = x.shape
+        dev = x.device
+        with torch.cuda.device(dev):
+            self.prepare_train(dev)
+            self.flat_grad(dev)
+            self._tape, self._grads, self._keep, self._uses, self._emb_map = [], {}, [], {}, {}
+            S = D * H * W
+            x_cl = torch.zeros((N * S, _ld(C)), dtype=torch.bfloat16, device=dev)
+            ops.planar_to_cl(x.detach().float(), x_cl, C)
+            self._x_in = x_cl
+            out_cl = self.forward_cl(x_cl, timesteps.to(torch.int64).contiguous(), N, (D, H, W))
+            self._out_cl = out_cl
+            self._shape = (N, D, H, W)
+            out = torch.empty((N, m.out_channels, D, H, W), dtype=torch.float32, device=dev)
+            ops.cl_to_planar(out_cl, out, m.out_channels)
+        return out.to(x.dtype) if x.dtype != torch.float32 else out

@@ -102,6 +102,7 @@ class UNetEngine(WavUNetEngine):
             return self._buf(rows, width, dev)
 
         cats = [None] * n_in
+        enc_views = [None] * n_in                              # the encoder outputs as written (right-hand column slices)
         h, hdims = x_cl, tuple(dims)
         hs_dims = []
         for j, module in enumerate(m.input_blocks):
@@ -127,12 +128,14 @@ class UNetEngine(WavUNetEngine):
                     else:
                         h, hdims = self._resblock_u(layer, h, emb, N, hdims)
             cats[j] = cat
+            enc_views[j] = h
             hs_dims.append(hdims)
 
         # ---- bottleneck: the second block writes into the left slice of the first decoder input
         k_cat = n_in - 1
+        lefts = [cats[j][:, :plan[j][1]] for j in range(n_in)]      # decoder-side column slices (one view object each)
         h, hdims = self._resblock_u(m.middle_block[0], h, emb, N, hdims)
-        h, hdims = self._resblock_u(m.middle_block[1], h, emb, N, hdims, out=cats[k_cat][:, :plan[k_cat][1]])
+        h, hdims = self._resblock_u(m.middle_block[1], h, emb, N, hdims, out=lefts[k_cat])
 
         # ---- decoder
         for k, module in enumerate(m.output_blocks):
@@ -140,10 +143,14 @@ class UNetEngine(WavUNetEngine):
             if hs_dims[j] != hdims:
                 raise FcwdmError(f"skip connection {j} has spatial size {hs_dims[j]}, decoder has {hdims}")
             h = cats[j]                                          # == th.cat([h, hs.pop()], dim=1), already in place
-            cats[j] = None
-            nxt = cats[j - 1][:, :plan[j - 1][1]] if j > 0 else None
+            self._on_concat(h, lefts[j], enc_views[j], plan[j], N * hdims[0] * hdims[1] * hdims[2])
+            nxt = lefts[j - 1] if j > 0 else None
             for li, layer in enumerate(module):
                 last = li == len(module) - 1
                 h, hdims = self._resblock_u(layer, h, emb, N, hdims, out=nxt if last else None)
         return self._gn_silu_conv(m.out[0], h, m.out[2], N, hdims,
                                   out_ld=out_ld or max(8, (m.out_channels + 7) // 8 * 8))
+
+    def _on_concat(self, cat, left, right, plan_j, rows):
+        """Hook: `cat` (the decoder block's input) is the in-place concatenation of `left` (decoder tensor) and `right`
+        (encoder output); the training engine records the gradient split here."""

@@ -11,8 +11,7 @@ skip concatenation (unet.py:796) without a copy -- producers write straight into
 
 Supported flag set = what run.sh ships: dims=3, resblock_updown=True, no attention (attention_resolutions="",
 bottleneck_attention=False), use_scale_shift_norm=False, additive_skips=False, class_cond=False; resample_2d either
-way.  Anything else raises NotImplementedError at construction.  Inference only (sampling); calling it under autograd
-raises.
+way.  Anything else raises NotImplementedError at construction.  Sampling and training (autograd) are both served.
 """
 import torch as th
 import torch.nn as nn
@@ -201,6 +200,7 @@ class UNetModel(nn.Module):
         self.out = nn.Sequential(normalization(ch, num_groups), nn.SiLU(),
                                  zero_module(conv_nd(dims, model_channels, out_channels, 3, padding=1)))
         self._engine = None
+        self._train_engine = None
 
     # The reference's .to() supports a 2-device split and returns None (unet.py:727-752).  Here a 1-element list is
     # unwrapped, a real split is refused, and the module is returned as nn.Module.to does.
@@ -221,12 +221,26 @@ class UNetModel(nn.Module):
             object.__setattr__(self, "_engine", UNetEngine(self))
         return self._engine
 
+    def train_engine(self):
+        if getattr(self, "_train_engine", None) is None:
+            from fcwdm.train_engine import UNetTrainEngine
+            object.__setattr__(self, "_train_engine", UNetTrainEngine(self))
+        return self._train_engine
+
     def forward(self, x, timesteps, y=None):
-        """x: [N, C, D, H, W] fp32, timesteps: [N] -> [N, out_channels, D, H, W] (reference unet.py:754-800)."""
+        """x: [N, C, D, H, W] fp32, timesteps: [N] -> [N, out_channels, D, H, W] (reference unet.py:754-800).  Under
+        autograd with trainable parameters the forward is taped and the returned tensor carries one autograd node whose
+        backward runs the fcwdm backward kernels (as WavUNetModel does)."""
         assert y is None, "must specify y if and only if the model is class-conditional"
-        if th.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(
-                "UNetModel.forward under autograd: the fcwdm training path covers WavUNetModel (use_freq=True); the plain "
-                "UNetModel is inference-only here -- wrap sampling in torch.no_grad() (p_sample_loop does)")
         self.hs_shapes = []
+        if th.is_grad_enabled():
+            params = [p for p in self.parameters()]
+            if any(p.requires_grad for p in params):
+                if not all(p.requires_grad for p in params):
+                    raise NotImplementedError("partially frozen UNetModel: the fcwdm backward produces gradients for all "
+                                              "parameters or none")
+                from fcwdm.train_engine import WavUNetFunction
+                return WavUNetFunction.apply(self.train_engine(), x, timesteps, *params)
+            if x.requires_grad:
+                raise NotImplementedError("gradient w.r.t. the denoiser input is not implemented by the fcwdm backward")
         return self.engine().forward(x, timesteps)

@@ -263,6 +263,12 @@ int fcwdm_avgpool2_cl(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_
                       int64_t C, int pool_depth, void* stream);
 int fcwdm_upsample2_cl(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t N, int64_t D, int64_t H, int64_t W,
                        int64_t C, int up_depth, void* stream);
+/* their adjoints (training): dx[brick] = dy/(4 fd) (+ acc), (D,H,W) = dims of dy (pooled); dx = brick sums of dy (+ acc),
+ * (D,H,W) = dims of dy (up-sampled). */
+int fcwdm_avgpool2_cl_bwd(const void* dy, int64_t dy_ld, const void* acc, int64_t acc_ld, void* dx, int64_t dx_ld, int64_t N,
+                          int64_t D, int64_t H, int64_t W, int64_t C, int pool_depth, void* stream);
+int fcwdm_upsample2_cl_bwd(const void* dy, int64_t dy_ld, const void* acc, int64_t acc_ld, void* dx, int64_t dx_ld, int64_t N,
+                           int64_t D, int64_t H, int64_t W, int64_t C, int up_depth, void* stream);
 
 /* One-launch re-packing of all conv weights of a model.  jobs: device array of n_jobs records of 8 int64:
  * {src f32 master weight ptr, dst bf16 packed ptr, O, I, taps, pair, transposed, total}: O/I = output/input channels of

@@ -11,15 +11,18 @@ from . import diffusion as od
 from . import wunet as ow
 
 
-def training_step_grads(sd, tab, batch, t, noise, *, model_channels, channel_mult, contr="t1n", timestep_map=None):
+def training_step_grads(sd, tab, batch, t, noise, *, model_channels, channel_mult, contr="t1n", timestep_map=None,
+                        forward=None):
     """sd: state dict of fp32 tensors (tied keys share one tensor object).  Returns (loss, mse_wav, model_output,
-    grads) with grads[key] for every key of sd (tied keys share the accumulated gradient)."""
+    grads) with grads[key] for every key of sd (tied keys share the accumulated gradient).  forward: the denoiser
+    restatement (default oracle.wunet.wunet_forward; oracle.unet.unet_forward for the plain U-Net)."""
+    forward = forward or ow.wunet_forward
     leaves = {}
     for k, v in sd.items():
         if id(v) not in leaves:
             leaves[id(v)] = v.detach().clone().requires_grad_(True)
     live = {k: leaves[id(v)] for k, v in sd.items()}
-    model = lambda x, tt: ow.wunet_forward(live, x, tt, model_channels=model_channels, channel_mult=channel_mult)
+    model = lambda x, tt: forward(live, x, tt, model_channels=model_channels, channel_mult=channel_mult)
     terms, out, _ = od.training_losses(tab, model, batch, t, contr=contr, timestep_map=timestep_map, noise=noise)
     loss = (terms["mse_wav"] * torch.ones(8)).mean()                                   # train_util.py:447-449
     loss.backward()

@@ -178,3 +178,26 @@ def test_unet_small(golden):
     sd = ow.seeded_state_dict(shapes, seed=0)
     y = ou.unet_forward(sd, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), model_channels=32, channel_mult=(1, 2, 2))
     assert np.abs(y.numpy() - g["y"]).max() < 5e-5 * max(1.0, np.abs(g["y"]).max())
+
+
+def test_training_step_unet_small(golden):
+    """One reference training step of the plain UNetModel (train_unet_small.npz): loss and every parameter gradient."""
+    from oracle import train as otr
+    from oracle import unet as ou
+    g = golden("train_unet_small")
+    gu = golden("unet_small")
+    shapes = {str(k): tuple(int(v) for v in str(s).split(",")) for k, s in zip(gu["keys"], gu["shapes"])}
+    sd = ow.seeded_state_dict(shapes, seed=0)
+    tab, m10 = _tab10()
+    batch = {k: torch.from_numpy(g["batch_" + k]) for k in ("t1n", "t1c", "t2w", "t2f")}
+    loss, mse, out, grads = otr.training_step_grads(sd, tab, batch, torch.from_numpy(g["t"]), torch.from_numpy(g["noise"]),
+                                                    model_channels=32, channel_mult=(1, 2, 2), timestep_map=m10,
+                                                    forward=ou.unet_forward)
+    assert abs(float(loss) - float(g["loss"])) <= 2e-5 * float(g["loss"])
+    np.testing.assert_allclose(mse.numpy(), g["mse_wav"], rtol=2e-5)
+    for name, ref_norm in zip((str(n) for n in g["param_names"]), g["grad_norms"]):
+        gr = grads[name]
+        assert abs(float(gr.double().norm()) - ref_norm) <= 1e-3 * ref_norm + 1e-6, name
+        key = "grad/" + name if "grad/" + name in g.files else "gradslice/" + name
+        got = gr.numpy() if key.startswith("grad/") else gr[:2].numpy()
+        np.testing.assert_allclose(got, g[key], atol=1e-3 * float(np.abs(g[key]).max()) + 1e-7, err_msg=name)

@@ -39,7 +39,7 @@ def run_training_losses(diffusion, model, batch, t, noise):
     return loss, terms, mo
 
 
-def compare_grads(named_got, ref_of, ref_norms, label):
+def compare_grads(named_got, ref_of, ref_norms, label, rel_tol=8e-2):
     big = max(ref_norms.values())
     num = den = 0.0
     worst = (0.0, None)
@@ -55,7 +55,7 @@ def compare_grads(named_got, ref_of, ref_norms, label):
             cos = float((g * r).sum() / (g.norm() * r.norm()))
             if rel > worst[0]:
                 worst = (rel, name)
-            assert rel <= 8e-2 and cos >= 0.995, (label, name, rel, cos)
+            assert rel <= rel_tol and cos >= 0.995, (label, name, rel, cos)
     total = (num / den) ** 0.5
     print(f"{label}: all-parameter gradient rel-L2 {total:.3e}; worst tensor {worst[1]} {worst[0]:.3e}")
     assert total <= 4e-2, (label, total)
@@ -170,3 +170,70 @@ def test_fused_adamw_training_reduces_loss(golden):
                     np.testing.assert_allclose(got[mask], g[key][mask], atol=3e-4, err_msg=name)
     print("losses", losses)
     assert losses[-1] < losses[0]
+
+
+def test_unet_training_step_matches_reference_fixture(golden):
+    """The plain UNetModel (what run.sh's training actually instantiates) under autograd: taped UNetEngine plan, zero-copy
+    concat split in the backward, avg-pool / nearest adjoints -- against the reference's own training step."""
+    from guided_diffusion.script_util import create_gaussian_diffusion
+    from guided_diffusion.unet import UNetModel
+    from oracle.make_golden_unet import UNET_SMALL_CFG
+    g = golden("train_unet_small")
+    model = UNetModel(**UNET_SMALL_CFG)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(ow.seeded_state_dict(shapes, seed=0), strict=True)
+    model.to("cuda").train()
+    d10 = create_gaussian_diffusion(steps=10, predict_xstart=True, sample_schedule="sampled", mode="i2i")
+    batch = {k: torch.from_numpy(g["batch_" + k]) for k in ("t1n", "t1c", "t2w", "t2f")}
+    loss, terms, mo = run_training_losses(d10, model, batch, torch.from_numpy(g["t"]), torch.from_numpy(g["noise"]))
+    loss.backward()
+    torch.cuda.synchronize()
+    ref_loss = float(g["loss"])
+    print(f"plain unet loss {float(loss.detach()):.6f} vs reference {ref_loss:.6f}")
+    assert abs(float(loss) - ref_loss) <= 1e-2 * ref_loss
+    names = [str(n) for n in g["param_names"]]
+    norms = dict(zip(names, (float(v) for v in g["grad_norms"])))
+    params = dict(model.named_parameters())
+    assert sorted(params) == sorted(names)
+    for name in names:
+        if norms[name] >= 1e-3 * max(norms.values()):
+            got = float(params[name].grad.double().norm())
+            assert abs(got - norms[name]) <= 5e-2 * norms[name], (name, got, norms[name])
+    compare_grads({n: p.grad for n, p in params.items()},
+                  lambda n: torch.from_numpy(g["grad/" + n]) if "grad/" + n in g.files else None, norms,
+                  "plain unet fixture (full tensors)")
+    sl = {n: p.grad[:2] for n, p in params.items() if "gradslice/" + n in g.files}
+    sl_norms = {n: float(np.linalg.norm(g["gradslice/" + n].astype(np.float64))) for n in sl}
+    # two-output-channel slices of the deepest layers (2x2x2 voxels in this fixture: GroupNorm over 8 samples amplifies the
+    # bf16 rounding of the activations) get a wider per-tensor bound; direction (cosine >= 0.995) is still enforced
+    compare_grads(sl, lambda n: torch.from_numpy(g["gradslice/" + n]), sl_norms, "plain unet fixture (slices)", rel_tol=0.12)
+
+
+def test_unet_training_wide_matches_oracle():
+    """64 base channels: concat widths 128 / 192 / 256 (GroupNorm over 192 channels = 6 per group), CTA-pair dgrad."""
+    from guided_diffusion.script_util import create_gaussian_diffusion
+    from guided_diffusion.unet import UNetModel
+    from oracle import unet as ou
+    from oracle.make_golden_unet import UNET_SMALL_CFG
+    cfg = dict(UNET_SMALL_CFG, model_channels=64)
+    model = UNetModel(**cfg)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    sd = ow.seeded_state_dict(shapes, seed=4)
+    model.load_state_dict(sd, strict=True)
+    model.to("cuda").train()
+    d10 = create_gaussian_diffusion(steps=10, predict_xstart=True, sample_schedule="sampled", mode="i2i")
+    gen = torch.Generator().manual_seed(12)
+    batch = {k: torch.rand(1, 1, 16, 40, 24, generator=gen) for k in ("t1n", "t1c", "t2w", "t2f")}
+    t = torch.tensor([5])
+    noise = torch.randn(1, 1, 16, 40, 24, generator=gen)
+    loss, _, _ = run_training_losses(d10, model, batch, t, noise)
+    loss.backward()
+    torch.cuda.synchronize()
+    b10, m10 = od.respaced_betas(od.named_beta_schedule("linear", 10, "sampled"), od.space_timesteps(10, [10]))
+    ref_loss, _, _, ref_grads = otr.training_step_grads(sd, od.Tables(b10), batch, t, noise, model_channels=64,
+                                                        channel_mult=(1, 2, 2), timestep_map=m10, forward=ou.unet_forward)
+    print(f"plain unet (wide) loss {float(loss.detach()):.6f} vs oracle {float(ref_loss):.6f}")
+    assert abs(float(loss) - float(ref_loss)) <= 1e-2 * float(ref_loss)
+    params = dict(model.named_parameters())
+    norms = {n: float(ref_grads[n].double().norm()) for n in params}
+    compare_grads({n: p.grad for n, p in params.items()}, lambda n: ref_grads[n], norms, "plain unet oracle (64 channels)")
