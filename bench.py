@@ -525,12 +525,14 @@ def run_train(args):
     if rank == 0:
         samples = args.steps * world * B
         h2d = sum(v.numel() * 4 for v in host.values())
-        flop_step = 3.0 * CONV_FLOP_PER_STEP * B                             # fwd + dgrad + wgrad
+        model_name = "UNetModel" if MODEL["name"] == "unet" else "WavUNetModel"
+        flop_step = 3.0 * (UNET_FLOP_PER_STEP if MODEL["name"] == "unet" else CONV_FLOP_PER_STEP) * B   # fwd + dgrad + wgrad
         result = {
-            "metric": "WavUNetModel training samples/sec", "value": samples / (ms_res * 1e-3), "unit": "samples/s",
+            "metric": f"{model_name} training samples/sec", "value": samples / (ms_res * 1e-3), "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_res / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"training step (training_losses i2i + backward + AdamW), WavUNetModel CFG-W4, "
+            "config": {"workload": f"training step (training_losses i2i + backward + AdamW), {model_name} "
+                                   f"{'(run.sh: 1,2,2,4,4)' if MODEL['name'] == 'unet' else 'CFG-W4'}, "
                                    f"batch {B} x 224x224x160 per GPU, bf16 compute / fp32 master",
                        "parallelism": f"dp{world}: one bucketed NCCL gradient all-reduce (mean) per step" if world > 1
                        else "single GPU", "l2": "per-step activations ~6 GB >> 126 MB L2 (no flush needed)",
