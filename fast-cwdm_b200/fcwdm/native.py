@@ -9,7 +9,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfcwdm.so")
+LIB_PATH = os.environ.get("FCWDM_LIB_PATH") or os.path.join(_HERE, "libfcwdm.so")   # override: A/B runs of two builds
 
 _c_i64 = ctypes.c_int64
 _c_p = ctypes.c_void_p

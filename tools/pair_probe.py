@@ -59,3 +59,23 @@ for name, kw in (("pair+gn_in", dict(gn_in=(stats, gamma, beta, G, 1e-5))),
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     print(f"{name:18s} conv {D}x{H}x{W} {ci}->{co}: {ms*1e3:.1f} us {2.0*S*ci*co*27/ms/1e9:.1f} TFLOP/s", flush=True)
+
+# residual / channel-bias variants (the ResBlock's second conv: GN_IN + residual + output statistics)
+res = torch.randn((S, 64), device=dev).to(torch.bfloat16)
+cbias = torch.randn((1, 64), device=dev)
+for name, kw in (("pair+res", dict(residual=res)),
+                 ("pair+gn_in+res+stats", dict(gn_in=(stats, gamma, beta, G, 1e-5), residual=res, gn_stats=ostats, gn_groups=G)),
+                 ("pair+gn_in+cb+stats", dict(gn_in=(stats, gamma, beta, G, 1e-5), chan_bias=cbias, gn_stats=ostats, gn_groups=G))):
+    if co != 64:
+        continue
+    for _ in range(3):
+        ops.conv3d_pair_cl(x, wp, b, y, (1, D, H, W), ci, co, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ops.conv3d_pair_cl(x, wp, b, y, (1, D, H, W), ci, co, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    print(f"{name:22s} conv {D}x{H}x{W} {ci}->{co}: {ms*1e3:.1f} us {2.0*S*ci*co*27/ms/1e9:.1f} TFLOP/s", flush=True)
