@@ -277,6 +277,18 @@ int fcwdm_upsample2_cl_bwd(const void* dy, int64_t dy_ld, const void* acc, int64
  * max_total = the largest `total` (sizes the grid). */
 int fcwdm_conv3d_pack_all(const void* jobs, int64_t n_jobs, int64_t max_total, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * BraTS volume preprocessing (guided_diffusion/bratsloader.py:44-50,107-111: clip_and_normalize + pad + crop), V raw
+ * volumes (V, X, Y, Z) f32 -> (V, 1, X - 2*crop_x, Y - 2*crop_y, pad_z_to) f32 in [0, 1]:
+ *   lo, hi = np.quantile(x, q_lo), np.quantile(x, q_hi) ('linear' interpolation, exact order statistics by radix select)
+ *   out = (clip(x, lo, hi) - lo) / (hi - lo), zero-padded along Z, cropped in X and Y.
+ * quantiles: device float [V][2] output (lo, hi).  workspace: fcwdm_clip_normalize_workspace_bytes(V) device bytes.
+ * ---------------------------------------------------------------------------------------------------- */
+int64_t fcwdm_clip_normalize_workspace_bytes(int64_t V);
+int fcwdm_clip_normalize(const float* x, float* out, float* quantiles, void* workspace, int64_t workspace_bytes, int64_t V,
+                         int64_t X, int64_t Y, int64_t Z, int64_t crop_x, int64_t crop_y, int64_t pad_z_to, double q_lo,
+                         double q_hi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

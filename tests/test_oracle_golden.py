@@ -201,3 +201,15 @@ def test_training_step_unet_small(golden):
         key = "grad/" + name if "grad/" + name in g.files else "gradslice/" + name
         got = gr.numpy() if key.startswith("grad/") else gr[:2].numpy()
         np.testing.assert_allclose(got, g[key], atol=1e-3 * float(np.abs(g[key]).max()) + 1e-7, err_msg=name)
+
+
+def test_preprocess(golden):
+    """clip_and_normalize of the reference's loader (bratsloader.py:107-111) on two fixtures."""
+    from oracle import preprocess as op
+    g = golden("preprocess")
+    for k in ("vol", "neg"):
+        np.testing.assert_allclose(op.clip_and_normalize(g[k]), g[k + "_out"], rtol=0, atol=1e-15)
+    out = op.preprocess_volume(g["vol"], crop=4, pad_to=32)
+    assert out.shape == (1, 32, 28, 32) and out.dtype == np.float32
+    np.testing.assert_array_equal(out[0, :, :, :23], g["vol_out"][4:-4, 4:-4].astype(np.float32))
+    assert float(np.abs(out[..., 23:]).max()) == 0.0
