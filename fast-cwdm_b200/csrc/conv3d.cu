@@ -45,6 +45,7 @@ struct ConvArgs {
     double* gn_stats;   // [N][FCWDM_GN_STAT_REPLICAS][gn_groups][2] (pre-zeroed by the caller) or null
     int gn_cpg, gn_groups;
     int a_slots, b_stages;   // runtime split of shared memory between the halo-plane ring and the weight-tile ring
+    long long* trace;            // development: per-CTA clock64 stamps [grid][16] (fcwdm_debug_set_conv_trace), else null
     // GN_IN variant: the conv input is SiLU(GroupNorm(x)); the raw planes are normalised + activated in shared memory
     int Cin;                     // real input channels (multiple of 64, <= 256)
     const double* gi_stats;      // [N][FCWDM_GN_STAT_REPLICAS][gi_groups][2] statistics of x
@@ -179,12 +180,15 @@ __device__ __forceinline__ float c_silu(float x) {
     return x * fmaf(0.5f, t, 0.5f);
 }
 
+#define FCWDM_TRACE(slot) do { if (args.trace != nullptr) args.trace[(size_t)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+
 template <int N_TILE, int TD, int KS, bool GN_IN>
 __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_b,
                                                               const ConvArgs args) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: let the next kernel start its prologue
     using Cfg = ConvCfg<N_TILE, TD, KS>;
+    if (threadIdx.x == 0) FCWDM_TRACE(0);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t A_SLOTS = (uint32_t)args.a_slots, B_STAGES = (uint32_t)args.b_stages;
@@ -237,6 +241,7 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
     // PDL: barrier init, descriptor prefetch and TMEM allocation above overlapped the predecessor's tail; from here on
     // this kernel touches global memory, so wait for the predecessor to complete and flush.
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0) FCWDM_TRACE(1);
 
     if (warp == kWarpProdA) {
         // ================================ A producer: halo planes ================================
@@ -252,6 +257,7 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
                         mbar_arrive_expect_tx(land, Cfg::PLANE_BYTES);
                         tma_load_5d(smem_a + slot * Cfg::SLOT_BYTES, &map_a, land, cb * 64,
                                     tc.w0 - Cfg::PAD, tc.h0 - Cfg::PAD, tc.d0 + p - Cfg::PAD, tc.n);
+                        if (q == 0) FCWDM_TRACE(2);
                     }
                 }
             }
@@ -379,9 +385,11 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
 #pragma unroll
                     for (int j = 0; j < TD; ++j)
                         a_desc[j] = a_desc_base + (uint64_t)((((q_base + kd + j) % A_SLOTS) * Cfg::SLOT_BYTES) >> 4);
+                    if (r == 0 && lane == 0) FCWDM_TRACE(3);          // first planes have landed (and are transformed)
                     for (int kh = 0; kh < KS; ++kh, ++r) {
                         const uint32_t st = r % B_STAGES;
                         mbar_wait(full_b + 8 * st, (r / B_STAGES) & 1);
+                        if (r == 0 && lane == 0) FCWDM_TRACE(4);      // first weight stage has landed
                         tc_fence_after();
                         if (elect_one()) {
 #pragma unroll
@@ -414,6 +422,7 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
             }
             if (elect_one()) umma_commit(tmem_full + 8 * as);    // accumulators complete -> epilogue
             __syncwarp();
+            if (acc_it == 0 && lane == 0) FCWDM_TRACE(5);             // all MMAs of the first tile issued
         }
     } else if (warp < 4) {
         // ================================ epilogue ================================
@@ -453,6 +462,7 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
             }
             const uint32_t as = acc_it % Cfg::ACC_STAGES, aph = (acc_it / Cfg::ACC_STAGES) & 1;
             mbar_wait(tmem_full + 8 * as, aph);
+            if (acc_it == 0 && threadIdx.x == 0) FCWDM_TRACE(6);      // first tile's MMAs have retired
             tc_fence_after();
             const int h = tc.h0 + hh, w = tc.w0 + ww;
             const bool hw_ok = (h < args.H) && (w < args.W);
@@ -519,12 +529,14 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + 8 * as);
+            if (acc_it == 0 && threadIdx.x == 0) FCWDM_TRACE(7);      // first tile stored
         }
         if (want_stats && cur_n >= 0) flush_gn_stats(wstat, args, cur_n, ew, lane);
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) FCWDM_TRACE(8);
     if (warp == kWarpAlloc) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -554,6 +566,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
+static long long* g_conv_trace = nullptr;     // development only (fcwdm_debug_set_conv_trace)
 
 template <int N_TILE, int TD, int KS>
 static cudaError_t set_attr() {
@@ -724,6 +737,7 @@ static int conv3d_fwd_impl(const void* x, int64_t x_ld, const void* wp, const fl
     a.bias = bias; a.chan_bias = chan_bias; a.cb_ld = cb_ld;
     a.residual = (const __nv_bfloat16*)residual; a.res_ld = res_ld;
     a.y = (__nv_bfloat16*)y; a.y_ld = y_ld;
+    a.trace = g_conv_trace;
     a.gn_stats = gn_stats;
     a.gn_groups = gn_stats ? (int)gn_groups : 0;
     a.gn_cpg = gn_stats ? (int)(Cout / gn_groups) : 0;
@@ -781,4 +795,12 @@ extern "C" int fcwdm_conv3d_gn_fwd(const void* x, int64_t x_ld, const void* wp, 
     FCWDM_REQUIRE(gn_in_stats != nullptr, FCWDM_ERR_INVALID, "fcwdm_conv3d_gn_fwd: null input statistics");
     return conv3d_fwd_impl(x, x_ld, wp, bias, chan_bias, cb_ld, residual, res_ld, y, y_ld, gn_stats, gn_groups, gn_in_stats,
                            gn_in_gamma, gn_in_beta, gn_in_groups, gn_in_eps, N, D, H, W, Cin, Cout, 3, stream);
+}
+
+/* Development aid (tools/conv_trace.py): when set, every fcwdm_conv3d_fwd launch writes per-CTA clock64 stamps
+ * [grid][16] to this device buffer (0 entry, 1 after the dependency wait, 2 first plane requested, 3 first planes ready,
+ * 4 first weights ready, 5 first tile's MMAs issued, 6 retired, 7 stored, 8 exit).  NULL switches it off. */
+extern "C" int fcwdm_debug_set_conv_trace(void* device_buffer) {
+    g_conv_trace = (long long*)device_buffer;
+    return FCWDM_OK;
 }

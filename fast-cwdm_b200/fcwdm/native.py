@@ -68,6 +68,7 @@ PROTOTYPES = {
     "fcwdm_upsample2_cl_bwd": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64] + [_c_i64] * 5 + [_c_int, _c_p]),
     "fcwdm_clip_normalize_workspace_bytes": (_c_i64, [_c_i64]),
     "fcwdm_clip_normalize": (_c_int, [_c_p, _c_p, _c_p, _c_p, _c_i64] + [_c_i64] * 7 + [ctypes.c_double, ctypes.c_double, _c_p]),
+    "fcwdm_debug_set_conv_trace": (_c_int, [_c_p]),
 }
 
 FCWDM_F32, FCWDM_BF16 = 0, 1

@@ -289,6 +289,10 @@ int fcwdm_clip_normalize(const float* x, float* out, float* quantiles, void* wor
                          int64_t X, int64_t Y, int64_t Z, int64_t crop_x, int64_t crop_y, int64_t pad_z_to, double q_lo,
                          double q_hi, void* stream);
 
+/* Development aid: per-CTA clock64 stamps of the next fcwdm_conv3d_fwd launches into a device buffer [grid][16]
+ * (see csrc/conv3d.cu); NULL switches it off.  Not used by the product path. */
+int fcwdm_debug_set_conv_trace(void* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif
