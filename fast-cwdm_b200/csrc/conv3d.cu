@@ -45,6 +45,8 @@ struct ConvArgs {
     double* gn_stats;   // [N][FCWDM_GN_STAT_REPLICAS][gn_groups][2] (pre-zeroed by the caller) or null
     int gn_cpg, gn_groups;
     int a_slots, b_stages;   // runtime split of shared memory between the halo-plane ring and the weight-tile ring
+    int split;                   // split-K: cluster of `split` CTAs shares one tile, each takes n_cb / split channel blocks
+    int part_off;                // byte offset (from the barrier area) of the leader's fp32 partial-sum slots [split-1][N_TILE][128]
     long long* trace;            // development: per-CTA clock64 stamps [grid][16] (fcwdm_debug_set_conv_trace), else null
     // GN_IN variant: the conv input is SiLU(GroupNorm(x)); the raw planes are normalised + activated in shared memory
     int Cin;                     // real input channels (multiple of 64, <= 256)
@@ -182,7 +184,7 @@ __device__ __forceinline__ float c_silu(float x) {
 
 #define FCWDM_TRACE(slot) do { if (args.trace != nullptr) args.trace[(size_t)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
 
-template <int N_TILE, int TD, int KS, bool GN_IN>
+template <int N_TILE, int TD, int KS, bool GN_IN, bool SPLITK>
 __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_b,
                                                               const ConvArgs args) {
@@ -192,6 +194,14 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t A_SLOTS = (uint32_t)args.a_slots, B_STAGES = (uint32_t)args.b_stages;
+    // split-K (low-resolution layers: one tile per CTA is a serial chain of n_cb * 27 * 4 MMAs of >= 61 cycles each,
+    // tools/mma_bench.cu): a cluster of `split` CTAs shares a tile, CTA `crank` accumulates channel blocks
+    // [cb0, cb1) in its own tensor memory, the non-leaders then add their fp32 partials into the leader's
+    // shared-memory buffer (red.shared::cluster) and the leader runs the epilogue.
+    const int split = SPLITK ? args.split : 1;       // compile-time 1 for the ordinary instantiation: all split-K code folds away
+    const int crank = split > 1 ? (int)cluster_ctarank() : 0;
+    const int tile0 = (int)blockIdx.x / split, tile_step = (int)gridDim.x / split;
+    const int cb0 = crank * (args.n_cb / split), cb1 = cb0 + args.n_cb / split;
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_a + A_SLOTS * Cfg::SLOT_BYTES;
     const uint32_t bars = smem_b + B_STAGES * Cfg::B_BYTES;
@@ -203,7 +213,9 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
     const uint32_t tmem_full = empty_b + 8 * B_STAGES;
     const uint32_t tmem_empty = tmem_full + 8 * Cfg::ACC_STAGES;
     const uint32_t landed_a = tmem_empty + 8 * Cfg::ACC_STAGES;    // [A_SLOTS] GN_IN: TMA has written the raw plane
-    const uint32_t tmem_slot = landed_a + 8 * A_SLOTS;             // 4 B: TMEM base address
+    const uint32_t part_ready = landed_a + 8 * A_SLOTS;            // leader: all non-leaders have added their partials
+    const uint32_t part_free = part_ready + 8;                     // non-leader: the leader's buffer is zeroed for this tile
+    const uint32_t tmem_slot = part_free + 8;                      // 4 B: TMEM base address
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* sbias = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));   // [N_TILE] bias + chan_bias of the current tile
     float* wstat = reinterpret_cast<float*>(smem_raw + (bars + 1536 - smem_u32(smem_raw)));   // [4 warps][32 groups][2]
@@ -218,6 +230,8 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
             mbar_init(empty_a + 8 * i, 1);
             mbar_init(landed_a + 8 * i, 1);
         }
+        mbar_init(part_ready, 4 * (split > 1 ? split - 1 : 1));
+        mbar_init(part_free, 4);
         for (int i = 0; i < B_STAGES; ++i) {
             mbar_init(full_b + 8 * i, 1);
             mbar_init(empty_b + 8 * i, 1);
@@ -236,6 +250,7 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
     if (warp == kWarpAlloc) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (split > 1) cluster_sync_all();       // every CTA's barriers exist before anybody signals across the cluster
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     // PDL: barrier init, descriptor prefetch and TMEM allocation above overlapped the predecessor's tail; from here on
@@ -247,9 +262,9 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
         // ================================ A producer: halo planes ================================
         if (lane == 0) {
             uint32_t q = 0;
-            for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < args.num_tiles; tile += tile_step) {
                 const TileCoord tc = decode_tile(tile, args, TD, N_TILE);
-                for (int cb = 0; cb < args.n_cb; ++cb) {
+                for (int cb = cb0; cb < cb1; ++cb) {
                     for (int p = 0; p < Cfg::PLANES; ++p, ++q) {
                         const uint32_t slot = q % A_SLOTS, ph = (q / A_SLOTS) & 1;
                         mbar_wait(empty_a + 8 * slot, ph ^ 1);
@@ -266,9 +281,9 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
         // ================================ B producer: weight tiles ================================
         if (lane == 0) {
             uint32_t r = 0;
-            for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < args.num_tiles; tile += tile_step) {
                 const TileCoord tc = decode_tile(tile, args, TD, N_TILE);
-                for (int cb = 0; cb < args.n_cb; ++cb) {
+                for (int cb = cb0; cb < cb1; ++cb) {
                     for (int tap = 0; tap < Cfg::TAPS; tap += KS, ++r) {
                         const uint32_t st = r % B_STAGES, ph = (r / B_STAGES) & 1;
                         mbar_wait(empty_b + 8 * st, ph ^ 1);
@@ -290,7 +305,7 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
         const int jmine = (pt & 7) ^ ((pt >> 3) & 7);
         int cur_n = -1;
         uint32_t q = 0;
-        for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < args.num_tiles; tile += tile_step) {
             const TileCoord tc = decode_tile(tile, args, TD, N_TILE);
             if (tc.n != cur_n) {
                 cur_n = tc.n;
@@ -315,7 +330,7 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
                 }
                 asm volatile("bar.sync 2, 128;" ::: "memory");
             }
-            for (int cb = 0; cb < args.n_cb; ++cb) {
+            for (int cb = cb0; cb < cb1; ++cb) {
                 float sc[8], sh[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -367,12 +382,12 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
         const uint64_t a_desc_base = make_sw128_desc(smem_a, Cfg::ROWP * 128);
         const uint64_t b_desc_base = make_sw128_desc(smem_b, 1024);
         uint32_t q_base = 0, r = 0, acc_it = 0;
-        for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++acc_it) {
+        for (int tile = tile0; tile < args.num_tiles; tile += tile_step, ++acc_it) {
             const uint32_t as = acc_it % Cfg::ACC_STAGES, aph = (acc_it / Cfg::ACC_STAGES) & 1;
             mbar_wait(tmem_empty + 8 * as, aph ^ 1);
             tc_fence_after();
             const uint32_t acc0 = tmem_base + as * Cfg::ACC_COLS;
-            for (int cb = 0; cb < args.n_cb; ++cb) {
+            for (int cb = cb0; cb < cb1; ++cb) {
                 int planes_ready = 0;
                 for (int kd = 0; kd < KS; ++kd) {
                     while (planes_ready < kd + TD) {
@@ -396,7 +411,7 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
                             for (int kw = 0; kw < KS; ++kw) {
                                 const uint64_t b_desc = b_desc_base + (uint64_t)((st * Cfg::B_BYTES + kw * Cfg::B_TAP_BYTES) >> 4);
                                 const uint64_t tap_off = (uint64_t)(((kh * Cfg::ROWP + kw) * 128) >> 4);
-                                const uint32_t first = ((cb == 0) && (kd == 0) && (kh == 0) && (kw == 0)) ? 0u : 1u;
+                                const uint32_t first = ((cb == cb0) && (kd == 0) && (kh == 0) && (kw == 0)) ? 0u : 1u;
 #pragma unroll
                                 for (int j = 0; j < TD; ++j) {
                                     const uint64_t ad = a_desc[j] + tap_off;
@@ -440,8 +455,48 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
         }
         int cur_n = -1, cur_n0 = -1;
         uint32_t acc_it = 0;
-        for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++acc_it) {
+        // split-K: the leader's partial-sum slots [split-1][N_TILE][128] fp32 (column-major: lanes hit consecutive banks)
+        const uint32_t part_u32 = bars + (uint32_t)args.part_off;
+        float* part = reinterpret_cast<float*>(smem_raw + (part_u32 - smem_u32(smem_raw)));
+        if (split > 1 && crank == 0) {
+            __syncwarp();
+            if (lane == 0)
+                for (int r = 1; r < split; ++r) mbar_arrive_cluster(mapa_u32(part_free, (uint32_t)r));
+        }
+        for (int tile = tile0; tile < args.num_tiles; tile += tile_step, ++acc_it) {
             const TileCoord tc = decode_tile(tile, args, TD, N_TILE);
+            if (split > 1 && crank != 0) {
+                // ---- non-leader: add this CTA's partial accumulator into the leader's buffer, nothing else
+                const uint32_t as = acc_it % Cfg::ACC_STAGES, aph = (acc_it / Cfg::ACC_STAGES) & 1;
+                mbar_wait(tmem_full + 8 * as, aph);
+                tc_fence_after();
+                mbar_wait(part_free, acc_it & 1);                          // the leader has zeroed the buffer for this tile
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * Cfg::ACC_COLS;
+                // plain (coalesced) distributed-shared-memory stores into this CTA's own slot of the leader's buffer
+                // [split-1][N_TILE][128]: remote atomics into one shared slot serialise (measured: 26 us for 3 x 8192 reds)
+                const uint32_t dst = mapa_u32(part_u32 + (uint32_t)(crank - 1) * (uint32_t)(N_TILE * 512), 0u) + (uint32_t)row * 4u;
+#pragma unroll 1
+                for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                    uint32_t acc[32];
+                    tmem_ld_x16(taddr + c0, acc);
+                    if (N_TILE > 16) tmem_ld_x16(taddr + c0 + 16, acc + 16);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (c0 + e < N_TILE)
+                            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst + (uint32_t)(c0 + e) * 512u),
+                                         "f"(__uint_as_float(acc[e]))
+                                         : "memory");
+                }
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(tmem_empty + 8 * as);
+                    mbar_arrive_cluster(mapa_u32(part_ready, 0u));
+                }
+                continue;
+            }
             if (tc.n != cur_n || tc.n0 != cur_n0) {
                 if (want_stats && tc.n != cur_n && cur_n >= 0) flush_gn_stats(wstat, args, cur_n, ew, lane);
                 cur_n = tc.n;
@@ -464,6 +519,10 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
             mbar_wait(tmem_full + 8 * as, aph);
             if (acc_it == 0 && threadIdx.x == 0) FCWDM_TRACE(6);      // first tile's MMAs have retired
             tc_fence_after();
+            if (split > 1) {                                              // every non-leader has added its partial sums
+                mbar_wait(part_ready, acc_it & 1);
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            }
             const int h = tc.h0 + hh, w = tc.w0 + ww;
             const bool hw_ok = (h < args.H) && (w < args.W);
 #pragma unroll 1
@@ -488,6 +547,14 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
 #pragma unroll
                     for (int q = 0; q < COLS; q += 16) tmem_ld_x16(taddr + c0 + q, acc + q);
                     tmem_ld_wait();
+                    if (split > 1) {                                          // + the other CTAs' partial sums
+                        for (int r = 0; r < split - 1; ++r) {
+                            const float* pr = part + r * (N_TILE * 128) + row;
+#pragma unroll
+                            for (int e = 0; e < COLS; ++e)
+                                acc[e] = __float_as_uint(__uint_as_float(acc[e]) + pr[(c0 + e) * 128]);
+                        }
+                    }
 #pragma unroll
                     for (int g = 0; g < COLS / 8; ++g) {
                         const int col = c0 + g * 8;
@@ -529,6 +596,12 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + 8 * as);
+            if (split > 1) {                                              // slots read: the next tile's partials may come
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                __syncwarp();
+                if (lane == 0)
+                    for (int r = 1; r < split; ++r) mbar_arrive_cluster(mapa_u32(part_free, (uint32_t)r));
+            }
             if (acc_it == 0 && threadIdx.x == 0) FCWDM_TRACE(7);      // first tile stored
         }
         if (want_stats && cur_n >= 0) flush_gn_stats(wstat, args, cur_n, ew, lane);
@@ -536,6 +609,7 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
 
     tc_fence_before();
     __syncthreads();
+    if (split > 1) cluster_sync_all();       // nobody exits while a peer may still signal its barriers / add into its buffer
     if (threadIdx.x == 0) FCWDM_TRACE(8);
     if (warp == kWarpAlloc) {
         tc_fence_after();
@@ -570,11 +644,17 @@ static long long* g_conv_trace = nullptr;     // development only (fcwdm_debug_s
 
 template <int N_TILE, int TD, int KS>
 static cudaError_t set_attr() {
-    cudaError_t e = cudaFuncSetAttribute(conv3d_igemm_kernel<N_TILE, TD, KS, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<N_TILE, TD, KS>::SMEM_BYTES);
-    if (e == cudaSuccess && KS == 3 && N_TILE >= 64)
-        e = cudaFuncSetAttribute(conv3d_igemm_kernel<N_TILE, TD, KS, (KS == 3 && N_TILE >= 64)>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<N_TILE, TD, KS>::SMEM_BYTES);
+    constexpr bool kGn = (KS == 3 && N_TILE >= 64);          // shapes with a fused-input-GroupNorm instantiation
+    constexpr bool kSp = (KS == 3 && TD == 1);               // shapes with a split-K (cluster) instantiation
+    constexpr int kBytes = ConvCfg<N_TILE, TD, KS>::SMEM_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(conv3d_igemm_kernel<N_TILE, TD, KS, false, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
+    if (e == cudaSuccess && kGn)
+        e = cudaFuncSetAttribute(conv3d_igemm_kernel<N_TILE, TD, KS, kGn, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
+    if (e == cudaSuccess && kSp)
+        e = cudaFuncSetAttribute(conv3d_igemm_kernel<N_TILE, TD, KS, false, kSp>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
+    if (e == cudaSuccess && kSp && kGn)
+        e = cudaFuncSetAttribute(conv3d_igemm_kernel<N_TILE, TD, KS, kGn, kSp>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
     return e;
 }
 
@@ -607,7 +687,24 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, ConvArgs a,
     const long long tiles = (long long)a.N * a.n_dt * a.n_ht * a.n_wt * a.n_nt;
     FCWDM_REQUIRE(tiles < (1ll << 31), FCWDM_ERR_UNSUPPORTED, "fcwdm_conv3d_fwd: too many tiles");
     a.num_tiles = (int)tiles;
-    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    // split-K across a cluster for the low-resolution layers: few tiles, long serial K chain (TD == 1 shapes only)
+    int split = 1;
+    {
+        static const int env_split = getenv("FCWDM_CONV_SPLITK") ? atoi(getenv("FCWDM_CONV_SPLITK")) : -1;
+        if (TD == 1 && KS == 3 && env_split != 0 && a.n_cb >= 2) {
+            auto fits = [&](int sp) {       // the leader's (sp - 1) partial slots + two weight stages + PLANES plane slots
+                return Cfg::SMEM_BUDGET - (sp - 1) * 128 * N_TILE * 4 - 2 * Cfg::B_BYTES >= Cfg::PLANES * Cfg::SLOT_BYTES;
+            };
+            for (int sp = 4; sp >= 2; sp >>= 1)
+                if (a.n_cb % sp == 0 && tiles * sp <= (long long)num_sms() && fits(sp)) { split = sp; break; }   // one wave
+            if (env_split > 0 && env_split <= 4 && a.n_cb % env_split == 0 && fits(env_split)) split = env_split;
+        }
+    }
+    a.split = split;
+    a.part_off = Cfg::TAIL_BYTES;
+    const int part_bytes = split > 1 ? (split - 1) * 128 * N_TILE * 4 : 0;
+    const int clusters = (int)(tiles < num_sms() / split ? tiles : num_sms() / split);
+    const int grid = clusters * split;
     // shared-memory split: the weight ring must cover the L2 round trip of one tile's weight stream (bytes in flight =
     // consumption rate x latency, ~64-96 KB); the halo-plane ring gets the rest (>= one tile's planes + 1 for overlap)
     {
@@ -615,22 +712,40 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, ConvArgs a,
         static const int env_a = getenv("FCWDM_CONV_ASLOTS") ? atoi(getenv("FCWDM_CONV_ASLOTS")) : 0;
         int b = env_b > 0 ? env_b : (KS == 1 ? 8 : (N_TILE >= 128 ? 2 : 4));      // stages of KS taps each
         if (b > Cfg::MAX_B_STAGES) b = Cfg::MAX_B_STAGES;
-        while (b > 2 && (Cfg::SMEM_BUDGET - b * Cfg::B_BYTES) / Cfg::SLOT_BYTES < Cfg::PLANES + 1) --b;
-        int as = (Cfg::SMEM_BUDGET - b * Cfg::B_BYTES) / Cfg::SLOT_BYTES;
+        const int budget = Cfg::SMEM_BUDGET - part_bytes;
+        while (b > 2 && (budget - b * Cfg::B_BYTES) / Cfg::SLOT_BYTES < Cfg::PLANES + 1) --b;
+        int as = (budget - b * Cfg::B_BYTES) / Cfg::SLOT_BYTES;
         if (env_a > 0 && env_a < as) as = env_a;
         if (as > Cfg::MAX_A_SLOTS) as = Cfg::MAX_A_SLOTS;
         if (as < TD + 1) as = TD + 1;
         a.a_slots = as;
         a.b_stages = b;
     }
+    constexpr bool kSp = (KS == 3 && TD == 1);
     if (a.gi_stats != nullptr) {
         if constexpr (KS == 3 && N_TILE >= 64) {
-            launch_k(conv3d_igemm_kernel<N_TILE, TD, KS, true>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, st, ma, mb, a);
+            if constexpr (kSp) {
+                if (split > 1) {
+                    launch_k_cluster(conv3d_igemm_kernel<N_TILE, TD, KS, true, true>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, st,
+                                     (unsigned)split, ma, mb, a);
+                    FCWDM_CHECK_LAUNCH("fcwdm_conv3d_fwd");
+                    return FCWDM_OK;
+                }
+            }
+            launch_k(conv3d_igemm_kernel<N_TILE, TD, KS, true, false>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, st, ma, mb, a);
         } else {
             FCWDM_REQUIRE(false, FCWDM_ERR_UNSUPPORTED, "fcwdm_conv3d_gn_fwd: fused input GroupNorm needs a 3x3x3 conv with C_out >= 64");
         }
     } else {
-        launch_k(conv3d_igemm_kernel<N_TILE, TD, KS, false>, dim3(grid), dim3(256), Cfg::SMEM_BYTES, st, ma, mb, a);
+        if constexpr (kSp) {
+            if (split > 1) {
+                launch_k_cluster(conv3d_igemm_kernel<N_TILE, TD, KS, false, true>, dim3(grid), dim3(256), Cfg::SMEM_BYTES, st,
+                                 (unsigned)split, ma, mb, a);
+                FCWDM_CHECK_LAUNCH("fcwdm_conv3d_fwd");
+                return FCWDM_OK;
+            }
+        }
+        launch_k(conv3d_igemm_kernel<N_TILE, TD, KS, false, false>, dim3(grid), dim3(256), Cfg::SMEM_BYTES, st, ma, mb, a);
     }
     FCWDM_CHECK_LAUNCH("fcwdm_conv3d_fwd");
     return FCWDM_OK;

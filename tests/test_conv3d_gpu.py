@@ -56,6 +56,10 @@ CASES = [
     (1, 6, 12, 24, 64, 128, 1),     # 1x1x1 skip conv
     (1, 2, 14, 10, 256, 128, 1),
     (1, 14, 14, 10, 128, 256, 3),   # 256 output channels
+    (1, 5, 7, 7, 256, 256, 3),      # bottleneck: one tile per CTA -> split-K over a 4-CTA cluster
+    (2, 10, 14, 14, 256, 256, 3),   # two samples, split-K 2 or 4
+    (1, 5, 7, 7, 1024, 256, 3),     # input-pyramid conv at the bottleneck: 16 channel blocks over 8 CTAs
+    (1, 5, 7, 7, 512, 64, 3),       # N_TILE = 64 single n-tile, 8 channel blocks
 ]
 
 
@@ -69,6 +73,9 @@ def test_conv3d_epilogue_fusions():
     got, ref = run_conv(2, 4, 16, 8, 64, 64, 3, use_bias=True, use_cb=True, use_res=True, seed=3)
     check(got, ref)
     got, ref = run_conv(1, 3, 9, 9, 64, 128, 1, use_bias=False, use_cb=False, use_res=True, seed=4)
+    check(got, ref)
+    # split-K cluster path (bottleneck shapes): the leader's epilogue carries bias, embedding and residual
+    got, ref = run_conv(2, 5, 7, 7, 256, 256, 3, use_bias=True, use_cb=True, use_res=True, seed=5)
     check(got, ref)
 
 
@@ -91,7 +98,8 @@ def test_conv3d_full_resolution_shape():
 
 
 @pytest.mark.parametrize("case", [(2, 5, 18, 10, 64, 64, 3, 32), (1, 4, 16, 16, 128, 128, 3, 32),
-                                  (1, 6, 10, 12, 64, 256, 1, 32), (2, 3, 7, 5, 32, 32, 3, 32)])
+                                  (1, 6, 10, 12, 64, 256, 1, 32), (2, 3, 7, 5, 32, 32, 3, 32),
+                                  (2, 5, 7, 7, 256, 256, 3, 32)])            # split-K: statistics from the leader only
 def test_conv3d_fused_groupnorm_statistics(case):
     """The epilogue's fused (sum, sumsq) per (n, group) of the stored bf16 output == statistics of that tensor."""
     from fcwdm import ops
