@@ -182,7 +182,13 @@ __device__ __forceinline__ float c_silu(float x) {
     return x * fmaf(0.5f, t, 0.5f);
 }
 
+// In-kernel clock stamps are compiled in only with -DFCWDM_CONV_TRACE (FCWDM_CONV_TRACE=1 python fcwdm/build.py --force):
+// even a never-taken branch in the MMA issue loop costs the ordinary build a few percent.
+#ifdef FCWDM_CONV_TRACE
 #define FCWDM_TRACE(slot) do { if (args.trace != nullptr) args.trace[(size_t)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+#else
+#define FCWDM_TRACE(slot) do { } while (0)
+#endif
 
 template <int N_TILE, int TD, int KS, bool GN_IN, bool SPLITK>
 __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -916,6 +922,14 @@ extern "C" int fcwdm_conv3d_gn_fwd(const void* x, int64_t x_ld, const void* wp, 
  * [grid][16] to this device buffer (0 entry, 1 after the dependency wait, 2 first plane requested, 3 first planes ready,
  * 4 first weights ready, 5 first tile's MMAs issued, 6 retired, 7 stored, 8 exit).  NULL switches it off. */
 extern "C" int fcwdm_debug_set_conv_trace(void* device_buffer) {
+#ifdef FCWDM_CONV_TRACE
     g_conv_trace = (long long*)device_buffer;
     return FCWDM_OK;
+#else
+    (void)device_buffer;
+    g_conv_trace = nullptr;
+    FCWDM_REQUIRE(device_buffer == nullptr, FCWDM_ERR_UNSUPPORTED,
+                  "fcwdm_debug_set_conv_trace: this build has no trace points (rebuild with FCWDM_CONV_TRACE=1)");
+    return FCWDM_OK;
+#endif
 }

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kTrThreads) gn_bwd_reduce_kernel(const __nv_bf
 // pass 2: dx = rstd * (gamma * dz - (S1 + x_hat * S2) / M) (+ acc), S1 = sum_{c in group} gamma_c A_c,
 // S2 = sum gamma_c B_c, M = S * channels_per_group; block (0, n) also adds A, B into dbeta, dgamma.
 template <bool kSilu>
-__global__ void __launch_bounds__(kTrThreads) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld,
+__global__ void __launch_bounds__(kTrThreads, 2) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld,
                                                                   const __nv_bfloat16* __restrict__ dy, int64_t dy_ld,
                                                                   const double* __restrict__ stats,
                                                                   const float* __restrict__ gamma,

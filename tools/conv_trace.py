@@ -1,5 +1,6 @@
 """Development probe: where does a low-resolution conv3d spend its time?  Per-CTA clock64 stamps (fcwdm_debug_set_conv_trace)
-of one launch with a cold L2, printed as medians over CTAs in microseconds from kernel entry."""
+of one launch with a cold L2, printed as medians over CTAs in microseconds from kernel entry.
+Needs a trace build of the library: FCWDM_CONV_TRACE=1 python fast-cwdm_b200/fcwdm/build.py --force"""
 import os
 import sys
 
