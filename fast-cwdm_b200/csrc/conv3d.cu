@@ -380,39 +380,42 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
             }
         }
     } else if (warp == kWarpMma) {
-        // ================================ MMA issuer (whole warp walks the loops; one elected lane issues) =======
+        // ================================ MMA issuer ================================================================
         // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
         // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) |
                                    ((uint32_t)(128 >> 4) << 24);
         const uint64_t a_desc_base = make_sw128_desc(smem_a, Cfg::ROWP * 128);
         const uint64_t b_desc_base = make_sw128_desc(smem_b, 1024);
-        uint32_t q_base = 0, r = 0, acc_it = 0;
-        for (int tile = tile0; tile < args.num_tiles; tile += tile_step, ++acc_it) {
-            const uint32_t as = acc_it % Cfg::ACC_STAGES, aph = (acc_it / Cfg::ACC_STAGES) & 1;
-            mbar_wait(tmem_empty + 8 * as, aph ^ 1);
-            tc_fence_after();
-            const uint32_t acc0 = tmem_base + as * Cfg::ACC_COLS;
-            for (int cb = cb0; cb < cb1; ++cb) {
-                int planes_ready = 0;
-                for (int kd = 0; kd < KS; ++kd) {
-                    while (planes_ready < kd + TD) {
-                        const uint32_t qq = q_base + planes_ready;
-                        mbar_wait(full_a + 8 * (qq % A_SLOTS), (qq / A_SLOTS) & 1);
-                        ++planes_ready;
-                    }
-                    // descriptors of the TD planes this kd touches (start-address field is in 16-byte units)
-                    uint64_t a_desc[TD];
+        // ONE elected lane runs the whole issue loop -- waits, MMAs and commits.  Re-electing per weight stage costs 160-250
+        // cycles per round (tools/mma_bench.cu: 12 MMAs per round 80 -> 63 cycles per MMA at N = 64, 24 per round 77 -> 69 at
+        // N = 128 with a single elected region): the tensor pipe drains at every re-entry of the elected branch.
+        if (elect_one()) {
+            uint32_t q_base = 0, r = 0, acc_it = 0;
+            for (int tile = tile0; tile < args.num_tiles; tile += tile_step, ++acc_it) {
+                const uint32_t as = acc_it % Cfg::ACC_STAGES, aph = (acc_it / Cfg::ACC_STAGES) & 1;
+                mbar_wait(tmem_empty + 8 * as, aph ^ 1);
+                tc_fence_after();
+                const uint32_t acc0 = tmem_base + as * Cfg::ACC_COLS;
+                for (int cb = cb0; cb < cb1; ++cb) {
+                    int planes_ready = 0;
+                    for (int kd = 0; kd < KS; ++kd) {
+                        while (planes_ready < kd + TD) {
+                            const uint32_t qq = q_base + planes_ready;
+                            mbar_wait(full_a + 8 * (qq % A_SLOTS), (qq / A_SLOTS) & 1);
+                            ++planes_ready;
+                        }
+                        // descriptors of the TD planes this kd touches (start-address field is in 16-byte units)
+                        uint64_t a_desc[TD];
 #pragma unroll
-                    for (int j = 0; j < TD; ++j)
-                        a_desc[j] = a_desc_base + (uint64_t)((((q_base + kd + j) % A_SLOTS) * Cfg::SLOT_BYTES) >> 4);
-                    if (r == 0 && lane == 0) FCWDM_TRACE(3);          // first planes have landed (and are transformed)
-                    for (int kh = 0; kh < KS; ++kh, ++r) {
-                        const uint32_t st = r % B_STAGES;
-                        mbar_wait(full_b + 8 * st, (r / B_STAGES) & 1);
-                        if (r == 0 && lane == 0) FCWDM_TRACE(4);      // first weight stage has landed
-                        tc_fence_after();
-                        if (elect_one()) {
+                        for (int j = 0; j < TD; ++j)
+                            a_desc[j] = a_desc_base + (uint64_t)((((q_base + kd + j) % A_SLOTS) * Cfg::SLOT_BYTES) >> 4);
+                        if (r == 0) FCWDM_TRACE(3);                   // first planes have landed (and are transformed)
+                        for (int kh = 0; kh < KS; ++kh, ++r) {
+                            const uint32_t st = r % B_STAGES;
+                            mbar_wait(full_b + 8 * st, (r / B_STAGES) & 1);
+                            if (r == 0) FCWDM_TRACE(4);               // first weight stage has landed
+                            tc_fence_after();
 #pragma unroll
                             for (int kw = 0; kw < KS; ++kw) {
                                 const uint64_t b_desc = b_desc_base + (uint64_t)((st * Cfg::B_BYTES + kw * Cfg::B_TAP_BYTES) >> 4);
@@ -429,22 +432,17 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
                             }
                             umma_commit(empty_b + 8 * st);   // weight stage (KS taps) free once these MMAs retire
                         }
-                        __syncwarp();
+                        // plane kd is not needed by later taps of this channel block
+                        umma_commit(empty_a + 8 * ((q_base + kd) % A_SLOTS));
                     }
-                    // plane kd is not needed by later taps of this channel block
-                    if (elect_one()) umma_commit(empty_a + 8 * ((q_base + kd) % A_SLOTS));
-                    __syncwarp();
-                }
-                if (elect_one()) {
                     for (int p = KS; p < Cfg::PLANES; ++p) umma_commit(empty_a + 8 * ((q_base + p) % A_SLOTS));
+                    q_base += Cfg::PLANES;
                 }
-                __syncwarp();
-                q_base += Cfg::PLANES;
+                umma_commit(tmem_full + 8 * as);    // accumulators complete -> epilogue
+                if (acc_it == 0) FCWDM_TRACE(5);                      // all MMAs of the first tile issued
             }
-            if (elect_one()) umma_commit(tmem_full + 8 * as);    // accumulators complete -> epilogue
-            __syncwarp();
-            if (acc_it == 0 && lane == 0) FCWDM_TRACE(5);             // all MMAs of the first tile issued
         }
+        __syncwarp();
     } else if (warp < 4) {
         // ================================ epilogue ================================
         const int ew = warp;                      // == warp % 4: TMEM lane quarter this warp may access
