@@ -1,4 +1,4 @@
-"""Data-parallel training over NCCL (needs >= 2 GPUs; skipped on a single-GPU box): tools/ddp_check.py under torchrun
+"""Data-parallel training over NCCL (needs >= 2 GPUs; skipped on a single-GPU box): tests/ddp_check.py under torchrun
 checks that the backward-overlapped bucketed all-reduce leaves every rank with the mean gradient."""
 import os
 import subprocess
@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_rank_nccl_gradient_mean():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29541", os.path.join(ROOT, "tools", "ddp_check.py")]
+           "--master-port", "29541", os.path.join(ROOT, "tests", "ddp_check.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     assert "max rel err" in p.stdout
