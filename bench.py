@@ -296,41 +296,14 @@ def run_gpu(args):
     def volume_resident():
         return pipeline.synthesize(diffusion, model, dev_vol[:, 1:2], dev_vol[:, 2:3], dev_vol[:, 3:4], dev_noise)
 
-    # end-to-end: host-resident inputs / outputs.  Two device input slots; the H2D copy of volume i+1 and the D2H
-    # copy of volume i-1 run on a copy stream underneath the compute of volume i (all inside the timed region).
-    copy_stream = torch.cuda.Stream(device)
-    slots = [(torch.empty_like(dev_vol), torch.empty_like(dev_noise)) for _ in range(2)]
-    h2d_done = [torch.cuda.Event() for _ in range(2)]
-    slot_free = [torch.cuda.Event() for _ in range(2)]
-    out_dev = [torch.empty((args.batch,) + IMAGE[:2] + (155,), dtype=torch.float32, device=device) for _ in range(2)]
-    state = {"i": 0, "primed": False}
-
-    def prefetch(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(slot_free[slot])          # the compute that read this slot has finished
-            slots[slot][0].copy_(host_vol, non_blocking=True)
-            slots[slot][1].copy_(host_noise, non_blocking=True)
-            h2d_done[slot].record(copy_stream)
+    # end-to-end: host-resident inputs / outputs through the package's own streaming API (fcwdm.pipeline.VolumeStream):
+    # the H2D copy of volume i+1 and the D2H copy of volume i-1 run on a copy stream underneath the compute of volume i
+    # (all inside the timed region).
+    stream = pipeline.VolumeStream(diffusion, model, device)
+    copy_stream = stream.copy_stream
 
     def volume_e2e():
-        cur = torch.cuda.current_stream(device)
-        slot = state["i"] % 2
-        if not state["primed"]:
-            for s in range(2):
-                slot_free[s].record(cur)
-            prefetch(slot)
-            state["primed"] = True
-        cur.wait_event(h2d_done[slot])
-        prefetch(1 - slot)                                   # next volume's inputs travel during this volume's compute
-        v, nz = slots[slot]
-        img = pipeline.synthesize(diffusion, model, v[:, 1:2], v[:, 2:3], v[:, 3:4], nz)
-        out_dev[slot].copy_(img)
-        slot_free[slot].record(cur)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(slot_free[slot])
-            host_out.copy_(out_dev[slot], non_blocking=True)  # D2H of the finished volume, off the compute stream
-        state["i"] += 1
-        return img
+        return stream.submit(host_vol, host_noise, host_out, next_case=(host_vol, host_noise))
 
     def barrier():
         torch.cuda.synchronize(device)
