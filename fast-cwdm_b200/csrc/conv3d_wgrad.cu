@@ -20,6 +20,8 @@
 // M = 64 MMAs; two taps then share a column range on interleaved datapath halves), and drains once at the end into a
 // per-split fp32 workspace.  A second kernel sums the splits (fixed order: deterministic) and scatters into the
 // reference's (C_out, C_in, k, k, k) fp32 gradient layout, optionally accumulating (weight-tied ResBlocks).
+#include <stdlib.h>
+
 #include "tc_ptx.cuh"
 
 namespace fcwdm {
@@ -224,6 +226,174 @@ __global__ void __launch_bounds__(256, 1) conv3d_wgrad_kernel(const __grid_const
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// C_out <= 64, C_in block of 64 (the full-resolution layers, 60 % of the wgrad FLOPs): tap-packed MMAs.
+//
+// One tcgen05.mma costs >= ~60 cycles whatever its shape (profiles/r01_mma_microbench.md), so a 64 x 64 x 16 MMA per
+// tap runs the tensor pipe at ~40 %.  Here the NINE taps of one kd are produced by TWO MMAs per K-step:
+//   dW[oh, ow] = sum_p dY[p + a] * X[p + b]   with tap (oh, ow) = b - a,
+//   A operand (M) = dY loaded with a halo in H only (18 x 8 voxels, row pitch 8 = 1024 B, every shift 1024-B aligned):
+//                   MMA 1 stacks the shifts a_h = -1 and a_h = 0 as two 64-channel chunks LBO = 1024 B apart (M = 128),
+//                   MMA 2 takes a_h = +1 alone (M = 64);
+//   B operand (N) = X loaded with a halo in W only (16 x 10 voxels): the shifts b_w = -1, 0, +1 are the three 64-channel
+//                   "chunks" of ONE N = 192 operand whose chunk stride (LBO) is a single voxel row, 128 B.
+//   MMA 1 -> taps (kh = 2, 1) x (kw = 0, 1, 2) in a 128-lane x 192-column accumulator, MMA 2 -> (kh = 0) x (kw = 0, 1, 2).
+// 16 instructions per tile instead of 72; accumulators: 192 + 192 tensor-memory columns.
+// ---------------------------------------------------------------------------------------------------
+struct Wg64Cfg {
+    static constexpr int DY_BYTES = 18 * 8 * 128;          // 18432, H-halo plane of dY
+    static constexpr int X_BYTES = 16 * 10 * 128;          // 20480, W-halo plane of X
+    static constexpr int STAGE_BYTES = DY_BYTES + X_BYTES; // 38912 (both 1024-B multiples)
+    static constexpr int STAGES = 5;
+    static constexpr int TMEM_COLS = 512;                  // 192 (M = 128) + 192 (M = 64) used
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 1024;
+};
+
+__global__ void __launch_bounds__(256, 1) conv3d_wgrad64_kernel(const __grid_constant__ CUtensorMap map_dy,
+                                                                const __grid_constant__ CUtensorMap map_x,
+                                                                const WgradArgs args) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    using Cfg = Wg64Cfg;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    const uint32_t full = bars;
+    const uint32_t empty = full + 8 * Cfg::STAGES;
+    const uint32_t done = empty + 8 * Cfg::STAGES;
+    const uint32_t tmem_slot = done + 8;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::STAGES; ++i) {
+            mbar_init(full + 8 * i, 1);
+            mbar_init(empty + 8 * i, 1);
+        }
+        mbar_init(done, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == kWgWarpProd && lane == 0) {
+        tma_prefetch_desc(&map_dy);
+        tma_prefetch_desc(&map_x);
+    }
+    if (warp == kWgWarpAlloc) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    const int split = blockIdx.x, n_split = gridDim.x;
+    const int kd = blockIdx.y;
+    const int ci0 = (blockIdx.z % args.n_nb) * 64;            // C_out <= 64: a single output-channel block
+
+    if (warp == kWgWarpProd) {
+        if (lane == 0) {
+            uint32_t q = 0;
+            for (int tile = split; tile < args.num_tiles; tile += n_split, ++q) {
+                int r = tile;
+                const int wt = r % args.n_wt; r /= args.n_wt;
+                const int ht = r % args.n_ht; r /= args.n_ht;
+                const int d = r % args.D;
+                const int n = r / args.D;
+                const uint32_t st = q % Cfg::STAGES, ph = (q / Cfg::STAGES) & 1;
+                mbar_wait(empty + 8 * st, ph ^ 1);
+                mbar_arrive_expect_tx(full + 8 * st, Cfg::STAGE_BYTES);
+                const uint32_t sa = smem_base + st * Cfg::STAGE_BYTES;
+                tma_load_5d(sa, &map_dy, full + 8 * st, 0, wt * 8, ht * 16 - 1, d, n);                         // H halo
+                tma_load_5d(sa + Cfg::DY_BYTES, &map_x, full + 8 * st, ci0, wt * 8 - 1, ht * 16, d + kd - 1, n);   // W halo
+            }
+        }
+    } else if (warp == kWgWarpMma) {
+        // D = f32, A = B = bf16, both MN-major; N = 192; M = 128 / 64
+        constexpr uint32_t idesc_common = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(192 >> 3) << 17);
+        constexpr uint32_t idesc128 = idesc_common | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc64 = idesc_common | ((uint32_t)(64 >> 4) << 24);
+        // A: 64-channel chunks 1024 B apart (the next H row of the halo plane), 8-row groups 1024 B apart (pitch 8)
+        const uint64_t a_base = make_sw128_mn_desc(smem_base, 1024, 1024);
+        // B: 64-channel chunks 128 B apart (the next voxel along W), 8-row groups 1280 B apart (pitch 10)
+        const uint64_t b_base = make_sw128_mn_desc(smem_base + Cfg::DY_BYTES, 128, 1280);
+        if (elect_one()) {
+            uint32_t q = 0;
+            for (int tile = split; tile < args.num_tiles; tile += n_split, ++q) {
+                const uint32_t st = q % Cfg::STAGES;
+                mbar_wait(full + 8 * st, (q / Cfg::STAGES) & 1);
+                tc_fence_after();
+                const uint64_t so = (uint64_t)((st * Cfg::STAGE_BYTES) >> 4);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const uint32_t acc = (q == 0 && s == 0) ? 0u : 1u;
+                    // output rows 2s, 2s+1: dY halo rows (2s + 1 + a_h); X rows 2s, 2s+1 (pitch 10)
+                    const uint64_t b = b_base + so + (uint64_t)((s * 2 * 1280) >> 4);
+                    umma_bf16(tmem_base, a_base + so + (uint64_t)(((2 * s + 0) * 1024) >> 4), b, idesc128, acc);          // a_h = -1, 0
+                    umma_bf16(tmem_base + 192, a_base + so + (uint64_t)(((2 * s + 2) * 1024) >> 4), b, idesc64, acc);     // a_h = +1
+                }
+                umma_commit(empty + 8 * st);
+            }
+            umma_commit(done);
+        }
+        __syncwarp();
+    } else if (warp < 4) {
+        mbar_wait(done, 0);
+        tc_fence_after();
+        const int ew = warp;
+        float* wsb = args.ws + (size_t)split * 27 * args.co_p * args.ci_p;
+        // region 1 (M = 128): lane r < 64 -> a_h = -1 (kh = 2), output channel r; r >= 64 -> a_h = 0 (kh = 1), channel r - 64
+        {
+            const int r = ew * 32 + lane;
+            const int kh = r < 64 ? 2 : 1;
+            const int co = r & 63;
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+            for (int kw = 0; kw < 3; ++kw) {
+                float* dst = wsb + ((size_t)((kd * 3 + kh) * 3 + kw) * args.co_p + co) * args.ci_p + ci0;
+#pragma unroll 1
+                for (int c = 0; c < 64; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_x16(taddr + kw * 64 + c, v);
+                    tmem_ld_x16(taddr + kw * 64 + c + 16, v + 16);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        *reinterpret_cast<float4*>(dst + c + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                              __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+                }
+            }
+        }
+        // region 2 (M = 64, columns 192..383): accumulator row r lives in lane (r % 16) + 32 * (r / 16): a_h = +1 (kh = 0)
+        {
+            const bool live = lane < 16;
+            const int co = ew * 16 + (lane & 15);
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + 192;
+#pragma unroll 1
+            for (int kw = 0; kw < 3; ++kw) {
+                float* dst = wsb + ((size_t)((kd * 3 + 0) * 3 + kw) * args.co_p + co) * args.ci_p + ci0;
+#pragma unroll 1
+                for (int c = 0; c < 64; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_x16(taddr + kw * 64 + c, v);
+                    tmem_ld_x16(taddr + kw * 64 + c + 16, v + 16);
+                    tmem_ld_wait();
+                    if (live) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4)
+                            *reinterpret_cast<float4*>(dst + c + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                                  __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kWgWarpAlloc) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+
 // dW[co][ci][tap] (+)= sum over splits of ws[split][tap][co][ci].  One block = one (tap, output channel, 32 input
 // channels): 8 thread groups stride over the splits with coalesced 128-byte reads, a shared-memory tree adds the 8
 // partial sums in a fixed order (deterministic), 32 threads scatter the result into the reference's layout.
@@ -332,6 +502,8 @@ int conv3d_wgrad_init_device() {
     FCWDM_WG_SET(64, 64, 3, 3) FCWDM_WG_SET(64, 128, 3, 1) FCWDM_WG_SET(128, 64, 3, 1) FCWDM_WG_SET(128, 128, 3, 1)
     FCWDM_WG_SET(64, 64, 1, 1) FCWDM_WG_SET(128, 64, 1, 1) FCWDM_WG_SET(128, 128, 1, 1)
 #undef FCWDM_WG_SET
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv3d_wgrad64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Wg64Cfg::SMEM_BYTES);
     FCWDM_REQUIRE(e == cudaSuccess, FCWDM_ERR_CUDA, "fcwdm_init: cudaFuncSetAttribute (wgrad) failed: %s",
                   cudaGetErrorString(e));
     return FCWDM_OK;
@@ -465,7 +637,35 @@ extern "C" int fcwdm_conv3d_wgrad(const void* x, int64_t x_ld, const void* dy, i
     a.ws = (float*)workspace;
     int rc = FCWDM_ERR_UNSUPPORTED;
     if (ksize == 3) {
-        if (p.m_tile == 64 && p.n_tile == 64 && p.nkh == 3) rc = launch_wgrad<64, 64, 3, 3>(mdy, mx, a, p, st);
+        if (p.m_tile == 64 && p.n_tile == 64 && p.nkh == 3) {
+            static const bool packed_off = getenv("FCWDM_WGRAD_PACKED") != nullptr && atoi(getenv("FCWDM_WGRAD_PACKED")) == 0;
+            if (packed_off) {
+                rc = launch_wgrad<64, 64, 3, 3>(mdy, mx, a, p, st);
+            } else {
+                // tap-packed kernel: dY with a halo in H only, X with a halo in W only
+                CUtensorMap mdy2, mx2;
+                cuuint32_t es[5] = {1, 1, 1, 1, 1};
+                cuuint64_t ddims[5] = {(cuuint64_t)dy_ld, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+                cuuint64_t dstr[4] = {(cuuint64_t)dy_ld * 2, (cuuint64_t)W * dy_ld * 2, (cuuint64_t)H * W * dy_ld * 2,
+                                      (cuuint64_t)D * H * W * dy_ld * 2};
+                cuuint32_t dbox[5] = {64, 8, 18, 1, 1};
+                CUresult r1 = g_wg_encode(&mdy2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), ddims, dstr, dbox, es,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                cuuint64_t xdims[5] = {(cuuint64_t)x_ld, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+                cuuint64_t xstr[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2,
+                                      (cuuint64_t)D * H * W * x_ld * 2};
+                cuuint32_t xbox[5] = {64, 10, 16, 1, 1};
+                CUresult r2 = g_wg_encode(&mx2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), xdims, xstr, xbox, es,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                FCWDM_REQUIRE(r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS, FCWDM_ERR_CUDA,
+                              "fcwdm_conv3d_wgrad: tensor map encode failed (%d, %d)", (int)r1, (int)r2);
+                launch_k(conv3d_wgrad64_kernel, dim3(p.n_split, 3, p.n_nb), dim3(256), Wg64Cfg::SMEM_BYTES, st, mdy2, mx2, a);
+                FCWDM_CHECK_LAUNCH("fcwdm_conv3d_wgrad");
+                rc = FCWDM_OK;
+            }
+        }
         else if (p.m_tile == 64 && p.n_tile == 128) rc = launch_wgrad<64, 128, 3, 1>(mdy, mx, a, p, st);
         else if (p.m_tile == 128 && p.n_tile == 64) rc = launch_wgrad<128, 64, 3, 1>(mdy, mx, a, p, st);
         else if (p.m_tile == 128 && p.n_tile == 128) rc = launch_wgrad<128, 128, 3, 1>(mdy, mx, a, p, st);
