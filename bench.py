@@ -520,7 +520,7 @@ def run_train(args):
         ach = flop / (ms_k * 1e-3) / 1e12
         result["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                               "frac": ach / peaks["tf_burst"], "traffic": None,
-                              "kernel": "conv3d_wgrad_kernel<64,64,3,3> + finalize, 64->64 @112x112x80",
+                              "kernel": "conv3d_wgrad64_kernel (tap-packed M=128/64 x N=192) + finalize, 64->64 @112x112x80",
                               "us_per_launch": ms_k * 1e3, "flop_per_launch": flop}
         result["cpu_baseline"] = None
         print(json.dumps(result))
