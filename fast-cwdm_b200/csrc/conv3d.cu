@@ -8,18 +8,23 @@
 // One CTA (256 threads, persistent over a static round-robin tile list) owns an output block of
 //   TD (depth) x 16 (H) x 8 (W) voxels  x  N_TILE output channels,
 // i.e. TD accumulators of 128 rows x N_TILE fp32 columns in tensor memory.  Per 64-channel block of C_in:
-//   * the A producer (warp 0, one lane) TMA-loads TD+2 halo planes (18 x 10 voxels x 64 ch = 18x10 rows of
+//   * the A producer (warp 4, one lane) TMA-loads TD+2 halo planes (18 x 10 voxels x 64 ch = 18x10 rows of
 //     128 B, SWIZZLE_128B, out-of-bounds rows zero-filled by the TMA unit = the conv's zero padding) into a
 //     ring of plane slots with per-slot full/empty mbarriers;
-//   * the B producer (warp 1, one lane) TMA-loads one [N_TILE x 64] weight tile per filter tap into its ring;
-//   * the MMA issuer (warp 2, one lane) walks the 27 taps; for tap (kd,kh,kw) and output plane j the A operand
-//     is the SAME halo plane slot (j+kd) read through a K-major SWIZZLE_128B UMMA descriptor whose start address
-//     is offset by (kh*10 + kw) rows and whose 8-row-group stride (SBO) is the halo row pitch (10 rows): every
-//     activation byte is fetched from L2 once per tile and reused for up to 27 taps x TD planes, and every
-//     weight tile is reused for TD x 128 voxels;  tcgen05.commit releases plane slots / weight stages;
-//   * the epilogue (warps 4-7) drains the accumulators with tcgen05.ld, adds bias (+ per-(n,c) timestep
-//     embedding) (+ residual), converts to bf16 and stores channels-last; a second TMEM accumulator stage lets
-//     it overlap the next tile's MMAs.
+//   * the B producer (warp 5, one lane) TMA-loads the three kw taps of one (kd, kh) -- [3][N_TILE x 64] -- per stage
+//     of its ring;
+//   * the MMA issuer (warp 7, ONE elected lane for the whole loop) walks the 27 taps; for tap (kd,kh,kw) and output
+//     plane j the A operand is the SAME halo plane slot (j+kd) read through a K-major SWIZZLE_128B UMMA descriptor
+//     whose start address is offset by (kh*10 + kw) rows and whose 8-row-group stride (SBO) is the halo row pitch
+//     (10 rows): every activation byte is fetched from L2 once per tile and reused for up to 27 taps x TD planes,
+//     and every weight tile is reused for TD x 128 voxels;  tcgen05.commit releases plane slots / weight stages;
+//   * the epilogue (warps 0-3 = the tensor-memory lane quarters) drains the accumulators with tcgen05.ld, adds bias
+//     (+ per-(n,c) timestep embedding) (+ residual), optionally accumulates the next GroupNorm's statistics,
+//     converts to bf16 and stores channels-last; a second TMEM accumulator stage lets it overlap the next tile's MMAs.
+// Template variants: GN_IN (384 threads: warps 8-11 normalise + SiLU-activate the landed planes in shared memory, so
+// the conv consumes SiLU(GroupNorm(x)) without a separate pass) and SPLITK (a cluster of 2 or 4 CTAs shares one tile
+// of a low-resolution layer, each takes a slice of the C_in blocks, partial sums travel through distributed shared
+// memory to the leader's epilogue).
 #include <stdlib.h>
 
 #include "tc_ptx.cuh"
