@@ -326,7 +326,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
                 }
                 fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(full_a_leader + 8 * slot);
+                if (lane == 0) mbar_arrive_remote(full_a_leader + 8 * slot);
             }
         }
     } else if (warp == kPWarpMma) {
@@ -400,7 +400,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
         tc_fence_before();
         __syncwarp();
         if (lane == 0)
-            for (int r = 0; r < Cfg::RING; ++r) mbar_arrive_cluster(acc_empty_leader + 8 * r);
+            for (int r = 0; r < Cfg::RING; ++r) mbar_arrive_remote(acc_empty_leader + 8 * r);
         int cur_n = -1;
         uint32_t G = 0;
         constexpr int HALF = N_TILE < 32 ? N_TILE : 32;          // accumulator columns drained per batch of TMEM loads
@@ -473,7 +473,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
                         tmem_st_wait();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8 * ring);
+                        if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8 * ring);
                     }
                     if (real) {                                           // warp-uniform
 #pragma unroll

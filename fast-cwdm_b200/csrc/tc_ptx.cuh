@@ -143,6 +143,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Remote arrive with the default (.release.cta) semantics, as CUTLASS's ClusterBarrier::arrive(cta_id) issues it: for
+// barriers that order tcgen05 / async-proxy work (which carry their own fences), not generic-proxy data written to a
+// peer's shared memory.  The .release.cluster form above costs MEMBAR.ALL.GPU + ERRBAR on every arrive -- it drains the
+// thread's outstanding global loads / stores -- and showed up as ~10% of the pair kernel's epilogue samples.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA loads issued by either CTA of a pair; completion bytes are credited to the LEADER CTA's barrier
 // (clearing bit 24 of the shared::cluster address selects the even CTA of the pair, as CUTLASS's
 // SM100_TMA_2SM_LOAD does with Sm100MmaPeerBitMask).
