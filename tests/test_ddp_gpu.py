@@ -1,5 +1,6 @@
 """Data-parallel training over NCCL (needs >= 2 GPUs; skipped on a single-GPU box): tests/ddp_check.py under torchrun
-checks that the backward-overlapped bucketed all-reduce leaves every rank with the mean gradient."""
+checks that the backward-overlapped bucketed all-reduce leaves every rank with the mean gradient;
+tests/trainloop_ddp_check.py runs the scripts/train.py sequence (dist_util + TrainLoop) with one process per GPU."""
 import os
 import subprocess
 import sys
@@ -18,3 +19,12 @@ def test_two_rank_nccl_gradient_mean():
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     assert "max rel err" in p.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_trainloop(tmp_path):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", os.path.join(ROOT, "tests", "trainloop_ddp_check.py"), str(tmp_path)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    assert "trainloop ddp ok" in p.stdout

@@ -1,0 +1,138 @@
+"""TrainLoop (the reference's training driver, train_util.py:32-462) on the fcwdm path: a few steps on the small
+configuration through the public surface scripts/train.py uses -- create_named_schedule_sampler, TrainLoop(...).run_loop()
+-- compared with the same steps written out by hand (training_losses + backward + FusedAdamW, what
+tests/test_train_gpu.py pins to the reference fixture), plus the checkpoint / resume cycle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wunet as ow
+from oracle.make_golden import SMALL_CFG
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("t1n", "t1c", "t2w", "t2f")
+
+
+class Volumes(torch.utils.data.Dataset):
+    """BRATSVolumes-shaped items (bratsloader.py:91-97) of random 16^3 volumes."""
+
+    def __init__(self, n=4, seed=5):
+        g = torch.Generator().manual_seed(seed)
+        self.items = [{k: torch.rand(1, 16, 16, 16, generator=g) for k in KEYS} for _ in range(n)]
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, i):
+        return dict(self.items[i], missing="none", subj="dummy_string")
+
+
+def fresh_model(seed=0):
+    from guided_diffusion.wunet import WavUNetModel
+    m = WavUNetModel(**SMALL_CFG)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(ow.tie_output_blocks(ow.seeded_state_dict(shapes, seed=seed), len(SMALL_CFG["channel_mult"])))
+    m.to("cuda")
+    m.train()
+    return m
+
+
+def make_loop(model, diffusion, steps, **kw):
+    from guided_diffusion.resample import create_named_schedule_sampler
+    from guided_diffusion.train_util import TrainLoop
+    data = torch.utils.data.DataLoader(Volumes(), batch_size=2, shuffle=False)
+    args = dict(model=model, diffusion=diffusion, data=data, batch_size=2, in_channels=32, image_size=16, microbatch=-1,
+                lr=1e-3, ema_rate="0.9999", log_interval=1, contr="t1n", save_interval=2, resume_checkpoint="",
+                resume_step=0, use_fp16=False, weight_decay=0.01, lr_anneal_steps=steps, dataset="brats",
+                schedule_sampler=create_named_schedule_sampler("uniform", diffusion, maxt=diffusion.num_timesteps),
+                summary_writer=None, mode="i2i", sample_schedule="sampled", diffusion_steps=10)
+    args.update(kw)
+    return TrainLoop(**args)
+
+
+def test_trainloop_matches_hand_written_steps_and_checkpoints(tmp_path, monkeypatch):
+    from guided_diffusion import logger
+    from guided_diffusion.script_util import create_gaussian_diffusion
+    from fcwdm.optim import FusedAdamW
+    monkeypatch.setenv("FCWDM_CHECKPOINT_ROOT", str(tmp_path))
+    logger.configure(dir=str(tmp_path / "log"), format_strs=["csv"])
+    STEPS = 4                                             # run_loop stops when step + resume_step reaches lr_anneal_steps
+    try:
+        d10 = create_gaussian_diffusion(steps=10, predict_xstart=True, sample_schedule="sampled", mode="i2i")
+        # ---- through TrainLoop
+        np.random.seed(0)
+        torch.manual_seed(0)
+        torch.cuda.manual_seed(0)
+        m1 = fresh_model()
+        loop = make_loop(m1, d10, STEPS)
+        loop.run_loop()
+        torch.cuda.synchronize()
+        assert loop.step == STEPS
+        # ---- the same three steps by hand
+        np.random.seed(0)
+        torch.manual_seed(0)
+        torch.cuda.manual_seed(0)
+        m2 = fresh_model()
+        opt = FusedAdamW(m2, lr=1e-3, weight_decay=0.01)
+        ones = torch.ones(8, device="cuda")
+        data = list(torch.utils.data.DataLoader(Volumes(), batch_size=2, shuffle=False))
+        losses = []
+        for s in range(1, STEPS):
+            batch = {k: data[(s - 1) % len(data)][k].cuda() for k in KEYS}
+            opt.zero_grad()
+            t = torch.from_numpy(np.random.choice(10, size=(2,), p=np.ones(10) / 10)).long().cuda()
+            terms, _, _ = d10.training_losses(m2, batch, t, model_kwargs={}, mode="i2i", contr="t1n")
+            loss = (terms["mse_wav"] * ones).mean()
+            loss.backward()
+            opt.step()
+            opt.param_groups[0]["lr"] = 1e-3 * (1 - s / STEPS)        # _anneal_lr (train_util.py:464-470)
+            losses.append(float(loss.detach()))
+        torch.cuda.synchronize()
+        rows = list(__import__("csv").DictReader(open(tmp_path / "log" / "progress.csv")))
+        got = [float(r["loss"]) for r in rows]
+        print("TrainLoop losses", got, "hand-written", losses)
+        assert len(got) == STEPS - 1
+        np.testing.assert_allclose(got, losses, rtol=2e-3)           # same kernels; fp32 atomics reorder a few sums
+        assert [int(float(r["step"])) for r in rows] == [1, 2, 3]
+        assert [int(float(r["samples"])) for r in rows] == [4, 6, 8]
+        assert all(np.isfinite(float(r["norm/grad_max"])) and float(r["norm/grad_max"]) > 0 for r in rows)
+        for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+            assert n1 == n2
+            assert float((p1 - p2).abs().max()) <= 2e-3 * max(1.0, float(p2.abs().max())), n1
+        assert abs(loop.opt.param_groups[0]["lr"] - 1e-3 * (1 - 3 / STEPS)) < 1e-12
+
+        # ---- checkpoints: best-of-run model + optimizer state + the best-loss table
+        ck = tmp_path / "checkpoints"
+        best = ck / "brats_t1n_BEST_sampled_10.pt"
+        assert best.exists() and (ck / "opt_best_t1n.pt").exists() and (ck / "best_losses.txt").exists()
+        table = dict(l.strip().split(":") for l in open(ck / "best_losses.txt"))
+        assert set(table) == {"t1n"} and float(table["t1n"]) == pytest.approx(min(got[1], got[2]), rel=1e-6)
+        sd = torch.load(best, map_location="cpu")
+        assert list(sd) == list(m1.state_dict())                       # the reference's key names, loadable as-is
+
+        # ---- resume: weights come back, the step counter is parsed from the file name, optimizer state is reloaded
+        m3 = fresh_model(seed=3)
+        loop3 = make_loop(m3, d10, 0, resume_checkpoint=str(best))
+        assert loop3.resume_step == 10                                   # "..._sampled_10.pt" -> 10, as in the reference
+        for k, v in m3.state_dict().items():
+            assert torch.equal(v.cpu(), sd[k]), k
+        assert loop3.opt.step_count == torch.load(ck / "opt_best_t1n.pt", map_location="cpu")["step"]
+        assert loop3.best_losses == {"t1n": float(table["t1n"])}
+        loop3.save()
+        assert (ck / f"brats_t1n_{loop3.step + 10:06d}_sampled_10.pt").exists()
+        assert (ck / f"opt{loop3.step + 10:06d}.pt").exists()
+    finally:
+        logger.reset()
+
+
+def test_trainloop_refuses_what_it_does_not_do(tmp_path, monkeypatch):
+    from guided_diffusion.script_util import create_gaussian_diffusion
+    monkeypatch.setenv("FCWDM_CHECKPOINT_ROOT", str(tmp_path))
+    d10 = create_gaussian_diffusion(steps=10, predict_xstart=True, sample_schedule="sampled", mode="i2i")
+    with pytest.raises(NotImplementedError):
+        make_loop(fresh_model(), d10, 2, use_fp16=True)
+    with pytest.raises(TypeError):
+        make_loop(torch.nn.Conv3d(1, 1, 3).cuda(), d10, 2)
