@@ -21,13 +21,21 @@ def build_cond(cond_1, cond_2, cond_3):
     return out
 
 
-def synthesize(diffusion, model, cond_1, cond_2, cond_3, noise, clip_denoised=True, crop=155, progress=False):
-    """Returns the synthesised modality (N, D, H, min(W, crop)) in [0, 1], masked by cond_1's background."""
+def synthesize(diffusion, model, cond_1, cond_2, cond_3, noise, clip_denoised=True, crop=155, progress=False,
+               post="sample"):
+    """Returns the synthesised modality (N, D, H, min(W, crop)).  post='sample': clamped to [0, 1] and masked by
+    cond_1's background (sample.py:113-125); post='auto': values <= 0.04 zeroed, nothing else (sample_auto.py:137)."""
     with torch.no_grad():
         cond = build_cond(cond_1, cond_2, cond_3)
         sample = diffusion.p_sample_loop(model, tuple(noise.shape), noise=noise, cond=cond,
                                          clip_denoised=clip_denoised, model_kwargs={}, progress=progress)
-        image = ops.sample_to_image(sample, cond_1)
+        if post == "sample":
+            image = ops.sample_to_image(sample, cond_1)
+        elif post == "auto":
+            image = ops.idwt3d_planar(sample, lll_scale=3.0, concat=True)
+            image = torch.where(image <= 0.04, torch.zeros_like(image), image)
+        else:
+            raise ValueError(f"unknown post-processing {post!r}")
     return image.squeeze(1)[:, :, :, :crop]
 
 
@@ -56,8 +64,9 @@ class VolumeStream:
         stream.finish()                                       # all results are in their out_host buffers
     """
 
-    def __init__(self, diffusion, model, device, raw=False, crop=155):
+    def __init__(self, diffusion, model, device, raw=False, crop=155, post="sample"):
         self.diffusion, self.model, self.device, self.raw, self.crop = diffusion, model, device, raw, crop
+        self.post = post
         self.copy_stream = torch.cuda.Stream(device)
         self._slots = None
         self._i = 0
@@ -108,7 +117,7 @@ class VolumeStream:
             N = v.shape[0]
             v = preprocess.clip_and_normalize(v.reshape((N * 4,) + tuple(v.shape[2:]))).reshape(
                 (N, 4) + (v.shape[2] - 16, v.shape[3] - 16, 160))
-        img = synthesize(self.diffusion, self.model, v[:, 1:2], v[:, 2:3], v[:, 3:4], nz, crop=self.crop)
+        img = synthesize(self.diffusion, self.model, v[:, 1:2], v[:, 2:3], v[:, 3:4], nz, crop=self.crop, post=self.post)
         self._out[slot].copy_(img)
         self._slot_free[slot].record(cur)
         with torch.cuda.stream(self.copy_stream):
