@@ -64,9 +64,15 @@ class VolumeStream:
         stream.finish()                                       # all results are in their out_host buffers
     """
 
-    def __init__(self, diffusion, model, device, raw=False, crop=155, post="sample"):
+    def __init__(self, diffusion, model, device, raw=False, crop=155, post="sample", file_order=False):
+        """file_order=True (with raw=True): volumes arrive as (N, 4, Z, Y, X) -- the NIfTI file order, first index
+        fastest -- and results leave as (N, crop, H, W), so the host never transposes a volume; the two axis swaps ride
+        on device copies that exist anyway (the contiguous() in front of the preprocessing, the D2H staging copy)."""
         self.diffusion, self.model, self.device, self.raw, self.crop = diffusion, model, device, raw, crop
         self.post = post
+        self.file_order = file_order
+        if file_order and not raw:
+            raise ValueError("file_order=True is for raw NIfTI volumes (raw=True)")
         self.copy_stream = torch.cuda.Stream(device)
         self._slots = None
         self._i = 0
@@ -115,10 +121,12 @@ class VolumeStream:
         if self.raw:
             from . import preprocess
             N = v.shape[0]
+            if self.file_order:
+                v = v.permute(0, 1, 4, 3, 2)                              # (N, 4, X, Y, Z) view of the file-order buffer
             v = preprocess.clip_and_normalize(v.reshape((N * 4,) + tuple(v.shape[2:]))).reshape(
                 (N, 4) + (v.shape[2] - 16, v.shape[3] - 16, 160))
         img = synthesize(self.diffusion, self.model, v[:, 1:2], v[:, 2:3], v[:, 3:4], nz, crop=self.crop, post=self.post)
-        self._out[slot].copy_(img)
+        self._out[slot].copy_(img.permute(0, 3, 2, 1) if self.file_order else img)
         self._slot_free[slot].record(cur)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._slot_free[slot])

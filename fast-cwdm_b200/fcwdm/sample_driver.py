@@ -79,7 +79,8 @@ class SamplingDriver:
         self.rank, self.world = rank, world_size
         self.seed = seed
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.depth = max(2, depth)
+        self.depth = max(2, depth, reader_threads)          # cases being read ahead of the GPU
+        self.n_writers = writer_threads
         self.write_target = write_target and mode == "sample"
         self.marker = subject_marker
         self.compresslevel = compresslevel
@@ -117,7 +118,7 @@ class SamplingDriver:
                     arr, hdr = nifti.read(case.files[m], dtype=np.float32, return_header=True)
                     if tuple(arr.shape) != RAW_SHAPE:
                         raise ValueError(f"{case.files[m]}: shape {arr.shape}, expected {RAW_SHAPE}")
-                    vol[0, c].copy_(torch.from_numpy(arr))
+                    vol[0, c].copy_(torch.from_numpy(arr.T))      # file order (Z, Y, X): a straight memcpy, no transpose
                     if c == 1:
                         case.header = hdr
                 else:
@@ -132,33 +133,39 @@ class SamplingDriver:
         return case
 
     # ------------------------------------------------------------------------------------------ stage 3: write
-    def _write_case(self, case, result, target, done_event, release):
+    def _write_case(self, case, result, target, done_event, release_in, release_out):
         t0 = time.time()
+        held_in = True
         try:
-            done_event.synchronize()                        # the D2H of this case has landed in `result`
+            done_event.synchronize()                        # this case's H2D and D2H are both done
+            release_in()                                    # ... so its input buffers can take the next read already
+            held_in = False
             n = 0
             if self.mode == "sample":
                 folder = os.path.join(self.output_dir, case.subject)
                 os.makedirs(folder, exist_ok=True)
-                n += nifti.write(os.path.join(folder, "sample.nii.gz"), result[0].numpy(), np.eye(4),
+                # buffers hold the volume in file order (Z, Y, X); .T is the (X, Y, Z) array, already Fortran-contiguous
+                n += nifti.write(os.path.join(folder, "sample.nii.gz"), result[0].numpy().T, np.eye(4),
                                  compresslevel=self.compresslevel)
                 if target is not None:
-                    n += nifti.write(os.path.join(folder, "target.nii.gz"), target[0].numpy(), np.eye(4),
+                    n += nifti.write(os.path.join(folder, "target.nii.gz"), target[0].numpy().T, np.eye(4),
                                      compresslevel=self.compresslevel)
             else:
                 folder = self.output_dir or os.path.dirname(case.files[conditions_for(case.contr)[0]])
                 if self.output_dir is not None:
                     folder = os.path.join(self.output_dir, case.subject)
                 os.makedirs(folder, exist_ok=True)
-                full = np.zeros(RAW_SHAPE, dtype=np.float32)              # pad back to 240 x 240 (sample_auto.py:143)
-                full[8:-8, 8:-8, :] = result[0].numpy()
-                n += nifti.write(os.path.join(folder, f"{case.subject}-{case.contr}.nii.gz"), full, like=case.header,
+                full = np.zeros(RAW_SHAPE[::-1], dtype=np.float32)        # pad back to 240 x 240 (sample_auto.py:143)
+                full[:, 8:-8, 8:-8] = result[0].numpy()
+                n += nifti.write(os.path.join(folder, f"{case.subject}-{case.contr}.nii.gz"), full.T, like=case.header,
                                  compresslevel=self.compresslevel)
             with self._lock:
                 self.stats["bytes_written"] += n
                 self.stats["cases"] += 1
         finally:
-            release()
+            if held_in:
+                release_in()
+            release_out()
             with self._lock:
                 self.stats["write_s"] += time.time() - t0
 
@@ -168,21 +175,22 @@ class SamplingDriver:
             model = self.models[contr]
             model.eval()
             self._streams[contr] = VolumeStream(self.diffusion, model, self.device, raw=True, crop=RAW_SHAPE[2],
-                                                post=self.mode)
+                                                post=self.mode, file_order=True)
         return self._streams[contr]
 
     def run(self):
         """Process this rank's cases; returns the statistics dict (cases written, bytes, stage times, wall time)."""
         t_start = time.time()
         pin = torch.cuda.is_available()
-        n_buf = self.depth + 2
-        free_in = queue.Queue()
-        free_out = queue.Queue()
-        for _ in range(n_buf):
-            free_in.put((torch.empty((1, 4) + RAW_SHAPE, dtype=torch.float32, pin_memory=pin),
+        free_in = queue.Queue()                             # pinned staging: inputs are held from read to upload,
+        free_out = queue.Queue()                            # outputs from download to the end of the file write
+        for _ in range(self.depth + 2):
+            free_in.put((torch.empty((1, 4) + RAW_SHAPE[::-1], dtype=torch.float32, pin_memory=pin),
                          torch.empty((1, 8, 112, 112, 80), dtype=torch.float32, pin_memory=pin)))
-            free_out.put((torch.empty((1, 224, 224, RAW_SHAPE[2]), dtype=torch.float32, pin_memory=pin),
-                          torch.empty((1, 224, 224, RAW_SHAPE[2]), dtype=torch.float32, pin_memory=pin)))
+        for _ in range(self.n_writers + 2):
+            free_out.put((torch.empty((1, RAW_SHAPE[2], 224, 224), dtype=torch.float32, pin_memory=pin),
+                          torch.empty((1, RAW_SHAPE[2], 224, 224), dtype=torch.float32, pin_memory=pin)
+                          if self.write_target else None))
         pending = []                                        # futures of cases being read, in order
         todo = list(self.my_indices)
         writes = []
@@ -219,12 +227,10 @@ class SamplingDriver:
                 done = torch.cuda.Event()
                 with torch.cuda.stream(stream.copy_stream):
                     done.record(stream.copy_stream)
-                # the input buffers may be reused once the H2D has been consumed: VolumeStream copies them into its own
-                # device slots before compute, and `done` is recorded after that on the same copy stream
-                def release(b=bufs, o=outs):
-                    free_in.put(b)
-                    free_out.put(o)
-                writes.append(self.writers.submit(self._write_case, case, out_host, target, done, release))
+                # `done` is recorded on the copy stream after this case's H2D and D2H: the writer releases the input
+                # buffers as soon as it fires and the output buffers after the files are written
+                writes.append(self.writers.submit(self._write_case, case, out_host, target, done,
+                                                  lambda b=bufs: free_in.put(b), lambda o=outs: free_out.put(o)))
             for s in self._streams.values():
                 s.finish()
         for w in writes:
@@ -236,8 +242,8 @@ class SamplingDriver:
     def _normalised_target(self, stream, case, tgt_host):
         """The ground-truth target as the loader would have normalised it, cropped like the sample (sample.py:133-136)."""
         from . import preprocess
-        raw = case.volume[0, :1].to(self.device, non_blocking=True)
-        tgt = preprocess.clip_and_normalize(raw)[:, 0, :, :, :RAW_SHAPE[2]]
+        raw = case.volume[0, :1].to(self.device, non_blocking=True).permute(0, 3, 2, 1)      # file order -> (1, X, Y, Z)
+        tgt = preprocess.clip_and_normalize(raw)[:, 0, :, :, :RAW_SHAPE[2]].permute(0, 3, 2, 1)
         cur = torch.cuda.current_stream(self.device)
         ev = torch.cuda.Event()
         ev.record(cur)

@@ -43,7 +43,7 @@ def main():
         for rep in range(2):                                  # the first pass includes kernel / graph warm-up
             out = os.path.join(root, f"out{rep}")
             drv = SamplingDriver(diffusion, model, ds.database, output_dir=out, mode="sample", contr="t1n",
-                                 reader_threads=rt, writer_threads=wt, depth=max(3, rt // 2))
+                                 reader_threads=rt, writer_threads=wt, depth=rt)
             st = drv.run()
             drv.close()
             print(f"pass {rep}: {st['cases']} cases in {st['wall_s']:.2f} s = {st['cases'] / st['wall_s']:.2f} cases/s "
