@@ -458,11 +458,44 @@ def run_train(args):
     def step_resident():
         step(dev_batch)
 
+    # e2e: every step uploads ITS batch from pinned host memory and its loss is read back on the host; the upload of
+    # step i+1 and the read-back of step i-1 ride on a copy stream underneath step i's compute (two device batch slots,
+    # two pinned loss cells), the way fcwdm.pipeline.VolumeStream does it for sampling
+    copy_stream = torch.cuda.Stream(device)
+    slots = [slot, {k: torch.empty_like(v) for k, v in dev_batch.items()}]
+    h2d_done = [torch.cuda.Event() for _ in range(2)]
+    slot_free = [torch.cuda.Event() for _ in range(2)]
+    loss_cell = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_done = [torch.cuda.Event() for _ in range(2)]
+    pipe = {"i": 0, "uploaded": -1}
+
+    def upload(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(slot_free[s])                             # the step that last read this slot is done
+            for k in slots[s]:
+                slots[s][k].copy_(host[k], non_blocking=True)                # H2D of step i's batch (pinned)
+            h2d_done[s].record(copy_stream)
+        pipe["uploaded"] = i
+
     def step_e2e():
-        for k in slot:
-            slot[k].copy_(host[k], non_blocking=True)                        # H2D of this step's batch (pinned)
-        step(slot)
-        last["host_loss"] = float(last["loss"])                              # D2H read of the step's result
+        i = pipe["i"]
+        s = i % 2
+        cur = torch.cuda.current_stream(device)
+        if pipe["uploaded"] < i:
+            upload(i)
+        cur.wait_event(h2d_done[s])
+        upload(i + 1)                                                        # next step's batch, under this step's compute
+        step(slots[s])
+        slot_free[s].record(cur)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(slot_free[s])
+            loss_cell[s].copy_(last["loss"], non_blocking=True)              # D2H of this step's result
+            loss_done[s].record(copy_stream)
+        if i > 0:
+            loss_done[1 - s].synchronize()
+            last["host_loss"] = float(loss_cell[1 - s])                      # the previous step's loss, on the host
+        pipe["i"] = i + 1
 
     def barrier():
         torch.cuda.synchronize(device)
@@ -493,8 +526,12 @@ def run_train(args):
     ms_res = timed(step_resident, args.steps, 0)
     launches = native.launch_count - n0
     clk = clocks.stop()
+    for ev in slot_free:
+        ev.record(torch.cuda.current_stream(device))
     ms_e2e = timed(step_e2e, args.steps, 1)
-    finite = bool(torch.isfinite(last["loss"]))
+    loss_done[(pipe["i"] - 1) % 2].synchronize()
+    last["host_loss"] = float(loss_cell[(pipe["i"] - 1) % 2])
+    finite = bool(torch.isfinite(last["loss"])) and last["host_loss"] == float(last["loss"])
     if rank == 0:
         samples = args.steps * world * B
         h2d = sum(v.numel() * 4 for v in host.values())
