@@ -191,8 +191,10 @@ __device__ __forceinline__ float c_silu(float x) {
 // even a never-taken branch in the MMA issue loop costs the ordinary build a few percent.
 #ifdef FCWDM_CONV_TRACE
 #define FCWDM_TRACE(slot) do { if (args.trace != nullptr) args.trace[(size_t)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+#define FCWDM_TRACE_ACC(slot, stmt) do { const long long t__ = clock64(); stmt; if (args.trace != nullptr) args.trace[(size_t)blockIdx.x * 16 + (slot)] += clock64() - t__; } while (0)
 #else
 #define FCWDM_TRACE(slot) do { } while (0)
+#define FCWDM_TRACE_ACC(slot, stmt) do { stmt; } while (0)
 #endif
 
 template <int N_TILE, int TD, int KS, bool GN_IN, bool SPLITK>
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
             uint32_t q_base = 0, r = 0, acc_it = 0;
             for (int tile = tile0; tile < args.num_tiles; tile += tile_step, ++acc_it) {
                 const uint32_t as = acc_it % Cfg::ACC_STAGES, aph = (acc_it / Cfg::ACC_STAGES) & 1;
-                mbar_wait(tmem_empty + 8 * as, aph ^ 1);
+                FCWDM_TRACE_ACC(11, mbar_wait(tmem_empty + 8 * as, aph ^ 1));   // trace: cycles waiting for a free accumulator
                 tc_fence_after();
                 const uint32_t acc0 = tmem_base + as * Cfg::ACC_COLS;
                 for (int cb = cb0; cb < cb1; ++cb) {
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
                     for (int kd = 0; kd < KS; ++kd) {
                         while (planes_ready < kd + TD) {
                             const uint32_t qq = q_base + planes_ready;
-                            mbar_wait(full_a + 8 * (qq % A_SLOTS), (qq / A_SLOTS) & 1);
+                            FCWDM_TRACE_ACC(10, mbar_wait(full_a + 8 * (qq % A_SLOTS), (qq / A_SLOTS) & 1));   // ... for planes
                             ++planes_ready;
                         }
                         // descriptors of the TD planes this kd touches (start-address field is in 16-byte units)
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
                         if (r == 0) FCWDM_TRACE(3);                   // first planes have landed (and are transformed)
                         for (int kh = 0; kh < KS; ++kh, ++r) {
                             const uint32_t st = r % B_STAGES;
-                            mbar_wait(full_b + 8 * st, (r / B_STAGES) & 1);
+                            FCWDM_TRACE_ACC(9, mbar_wait(full_b + 8 * st, (r / B_STAGES) & 1));   // ... for weight stages
                             if (r == 0) FCWDM_TRACE(4);               // first weight stage has landed
                             tc_fence_after();
 #pragma unroll

@@ -46,3 +46,6 @@ for gn_in in (False, True):
         print(f"\nconv {D}x{H}x{W} {ci}->{co} gn_in={gn_in}: {used.shape[0]} CTAs, event time {e0.elapsed_time(e1) * 1e3:.1f} us (cold L2)")
         for k, name in enumerate(NAMES):
             print(f"   {name:24s} {float(med[k]):8.2f} us")
+        acc = used[:, 9:12].double() / (clock_ghz * 1e3)                  # accumulated waits of the MMA-issuing thread
+        print(f"   MMA thread waited (median over CTAs): weights {float(acc[:, 0].median()):.2f} us, planes "
+              f"{float(acc[:, 1].median()):.2f} us, free accumulator {float(acc[:, 2].median()):.2f} us")
