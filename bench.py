@@ -63,7 +63,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_mark = index, [], None, 0.0
+
+    def mark(self):
+        """The timed region starts now: only samples arriving from here on are reported.  (The sampler is started
+        before the warm-up steps: nvidia-smi needs 0.3-1 s to produce its first line, longer than a short timed region.)"""
+        self.t_mark = time.time()
 
     def start(self):
         try:
@@ -76,16 +81,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is not None:
+            time.sleep(0.12)                       # let the sample covering the end of the region arrive
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if t >= self.t_mark]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         reasons = []
         for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
-            if any(len(r) > col and r[col].lower().startswith("active") for r in self.rows):
+            if any(len(r) > col and r[col].lower().startswith("active") for r in rows):
                 reasons.append(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
@@ -331,8 +338,9 @@ def run_gpu(args):
     torch.manual_seed(1234 + rank)
     clocks = ClockSampler(local)
     warm = max(args.warmup, 3)
-    timed(volume_resident, 0, warm)                      # lazy init, weight packing, CUDA-graph capture
     clocks.start()
+    timed(volume_resident, 0, warm)                      # lazy init, weight packing, CUDA-graph capture
+    clocks.mark()
     ms_res = timed(volume_resident, args.steps, 0)
     clk = clocks.stop()
     sampler = list(diffusion._samplers.values())[0]
@@ -519,9 +527,10 @@ def run_train(args):
         return float(ms)
 
     warm = max(args.warmup, 3)
-    timed(step_resident, 0, warm)
     clocks = ClockSampler(local)
     clocks.start()
+    timed(step_resident, 0, warm)
+    clocks.mark()
     n0 = native.launch_count
     ms_res = timed(step_resident, args.steps, 0)
     launches = native.launch_count - n0

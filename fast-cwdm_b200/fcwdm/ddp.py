@@ -7,6 +7,8 @@ trains single-process, train.py:26-29 -- nothing there does this).
 The training engine (fcwdm/train_engine.py) owns the flat gradient and calls ``ready(lo, hi)`` per parameter;
 ``GradSync`` only sees a flat tensor and ranges, so the bucketing logic is testable on CPU with gloo.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -35,11 +37,16 @@ class GradSync:
         self._works = []
         self.stream = torch.cuda.Stream(flat.device) if flat.is_cuda else None
         self.launched = 0
+        self._sent = [False] * len(self.buckets)
+        # FCWDM_DDP_OVERLAP=0: hold every bucket until finish() (one exchange after the backward instead of under it);
+        # a measurement knob -- NCCL's CTAs compete with the persistent conv kernels for SMs while they overlap
+        self.overlap = os.environ.get("FCWDM_DDP_OVERLAP", "1") != "0"
 
     def begin(self):
         self._pending = [b[2] for b in self.buckets]
         self._works = []
         self.launched = 0
+        self._sent = [False] * len(self.buckets)
 
     def _bucket_of(self, lo):
         import bisect
@@ -49,11 +56,12 @@ class GradSync:
         """Parameter range [lo, hi) holds its final local gradient (all producing kernels are enqueued)."""
         b = self._bucket_of(lo)
         self._pending[b] -= 1
-        if self._pending[b] == 0 and self.world > 1:
+        if self._pending[b] == 0 and self.world > 1 and self.overlap:
             self._launch(b)
 
     def _launch(self, b):
         lo, hi, _ = self.buckets[b]
+        self._sent[b] = True
         chunk = self.flat[lo:hi]
         avg = self.backend == "nccl"
         op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
@@ -71,8 +79,8 @@ class GradSync:
     def finish(self):
         """Join: every bucket reduced; the compute stream may read the averaged gradient afterwards."""
         if self.world > 1:
-            for b, pend in enumerate(self._pending):
-                if pend > 0:                                   # parameters that never reported (unused): reduce anyway
+            for b in range(len(self.buckets)):
+                if not self._sent[b]:                          # held back (overlap off) or never completed (unused params)
                     self._pending[b] = 0
                     self._launch(b)
             for w, chunk, avg in self._works:
