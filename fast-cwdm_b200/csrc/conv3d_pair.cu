@@ -358,14 +358,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
                         const uint32_t v = 5 - (Gt % 6);                    // lowest physical slot of the triple
                         const uint32_t d_addr = tmem_base + v * N_TILE;
                         const uint64_t a_plane = a_desc_base + (uint64_t)((slot * Cfg::SLOT_BYTES) >> 4);
+                        if (args.Cin > 32) {
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const uint64_t ad = a_plane + (uint64_t)((((tap / 3) * Cfg::ROWP + (tap % 3)) * 128) >> 4);
-                            const uint64_t bd = b_desc_base + (uint64_t)((tap * Cfg::B_TAP_BYTES) >> 4);
-                            umma_bf16_2sm(d_addr, ad, bd, idesc, 1u);
-                            umma_bf16_2sm(d_addr, ad + 2, bd + 2, idesc, 1u);
-                            umma_bf16_2sm(d_addr, ad + 4, bd + 4, idesc, 1u);
-                            umma_bf16_2sm(d_addr, ad + 6, bd + 6, idesc, 1u);
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint64_t ad = a_plane + (uint64_t)((((tap / 3) * Cfg::ROWP + (tap % 3)) * 128) >> 4);
+                                const uint64_t bd = b_desc_base + (uint64_t)((tap * Cfg::B_TAP_BYTES) >> 4);
+                                umma_bf16_2sm(d_addr, ad, bd, idesc, 1u);
+                                umma_bf16_2sm(d_addr, ad + 2, bd + 2, idesc, 1u);
+                                umma_bf16_2sm(d_addr, ad + 4, bd + 4, idesc, 1u);
+                                umma_bf16_2sm(d_addr, ad + 6, bd + 6, idesc, 1u);
+                            }
+                        } else {              // C_in <= 32 (the stem conv): channels 32..63 are padding, skip their K steps
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint64_t ad = a_plane + (uint64_t)((((tap / 3) * Cfg::ROWP + (tap % 3)) * 128) >> 4);
+                                const uint64_t bd = b_desc_base + (uint64_t)((tap * Cfg::B_TAP_BYTES) >> 4);
+                                umma_bf16_2sm(d_addr, ad, bd, idesc, 1u);
+                                umma_bf16_2sm(d_addr, ad + 2, bd + 2, idesc, 1u);
+                            }
                         }
                         umma_commit_2sm(empty_a + 8 * slot);                        // plane slot free (both CTAs)
                         const uint32_t Gc = G + k;                                  // output i = k is complete
