@@ -715,29 +715,56 @@ struct PackJob {            // mirrored by fcwdm/engine.py (8 x int64)
     long long total;        // packed elements
 };
 
+// One block = one tile of 512 (o, i) pairs x all taps, staged through shared memory so that BOTH sides are coalesced:
+// the master weight is read in runs that are contiguous in (inner channel, tap) -- 27 floats per (o, i) pair lie together --
+// and the packed tensor is written in runs that are contiguous in i.  Forward form: tile 8 o x 64 i (source rows = o);
+// data-gradient form: tile 16 o x 32 i (source rows = i, contiguous along o).  (The first version gathered one element
+// per thread with a 108-byte stride: 0.5 ms per training step for 54 M parameters; this one is bound by the 0.33 GB it moves.)
+constexpr int kPackPairs = 512;
+constexpr int kPackTapsMax = 27;
+
 __global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict__ jobs) {
     pdl_prologue();
+    __shared__ __nv_bfloat16 tile[kPackPairs * kPackTapsMax];
     const PackJob j = jobs[blockIdx.y];
     const int O = (int)j.O, I = (int)j.I, taps = (int)j.taps;
     const int O_p = j.pair ? (O <= 16 ? 16 : 64) : (O + 15) / 16 * 16;
     const int I_p = j.pair ? 64 : (I + 63) / 64 * 64;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < j.total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(idx % I_p);
-        long long r = idx / I_p;
-        const int o = (int)(r % O_p);
-        r /= O_p;
-        int tap;
-        if (j.pair) {
-            const int kd = (int)(r % 3), t2 = (int)(r / 3);
-            tap = kd * 9 + t2;
-        } else {
-            tap = (int)r;
+    const int TO = j.transposed ? 16 : 8, TI = kPackPairs / TO;
+    const int tiles_i = (I_p + TI - 1) / TI, tiles_o = (O_p + TO - 1) / TO;
+    const int run = (j.transposed ? TO : TI) * taps;              // source elements that are contiguous per source row
+    for (int t = blockIdx.x; t < tiles_o * tiles_i; t += gridDim.x) {
+        const int o0 = (t / tiles_i) * TO, i0 = (t % tiles_i) * TI;
+        __syncthreads();                                          // the previous tile has been written out
+        for (int e = threadIdx.x; e < kPackPairs * taps; e += blockDim.x) {
+            const int row = e / run, rem = e - row * run;         // source row inside the tile, offset inside its run
+            const int col = rem / taps, tap = rem - col * taps;
+            float v = 0.f;
+            int o_l, i_l, tap_d;
+            if (j.transposed) {                                   // w'[o][i][tap] = w[i][o][taps - 1 - tap]
+                i_l = row; o_l = col; tap_d = taps - 1 - tap;
+                if (i0 + i_l < I && o0 + o_l < O) v = j.src[((long long)(i0 + i_l) * O + o0) * taps + rem];
+            } else {
+                o_l = row; i_l = col; tap_d = tap;
+                if (o0 + o_l < O && i0 + i_l < I) v = j.src[((long long)(o0 + o_l) * I + i0) * taps + rem];
+            }
+            tile[(o_l * TI + i_l) * taps + tap_d] = __float2bfloat16_rn(v);
         }
-        float v = 0.f;
-        if (o < O && i < I)
-            v = j.transposed ? j.src[((long long)i * O + o) * taps + (taps - 1 - tap)] : j.src[((long long)o * I + i) * taps + tap];
-        j.dst[idx] = __float2bfloat16_rn(v);
+        __syncthreads();
+        for (int f = threadIdx.x; f < kPackPairs * taps; f += blockDim.x) {
+            const int tap = f / kPackPairs, p = f - tap * kPackPairs;
+            const int o = o0 + p / TI, i = i0 + p % TI;
+            if (o < O_p && i < I_p) {
+                long long idx;
+                if (j.pair) {
+                    const int kd = tap / 9, t2 = tap - kd * 9;    // pair layout: [kh*3+kw][kd][O_p][64]
+                    idx = (((long long)t2 * 3 + kd) * O_p + o) * 64 + i;
+                } else {
+                    idx = ((long long)tap * O_p + o) * I_p + i;
+                }
+                j.dst[idx] = tile[p * taps + tap];
+            }
+        }
     }
 }
 
@@ -747,8 +774,8 @@ extern "C" int fcwdm_conv3d_pack_all(const void* jobs, int64_t n_jobs, int64_t m
     FCWDM_REQUIRE(jobs != nullptr || n_jobs == 0, FCWDM_ERR_INVALID, "fcwdm_conv3d_pack_all: null job table");
     FCWDM_REQUIRE(n_jobs >= 0 && n_jobs <= 65535 && max_total >= 0, FCWDM_ERR_INVALID, "fcwdm_conv3d_pack_all: bad argument");
     if (n_jobs == 0 || max_total == 0) return FCWDM_OK;
-    long long bx = (max_total + 256 * 8 - 1) / (256 * 8);
-    if (bx > 1024) bx = 1024;
+    long long bx = (max_total + fcwdm::kPackPairs * 27 - 1) / (fcwdm::kPackPairs * 27);   // tiles of the largest 3x3x3 job
+    if (bx > 2048) bx = 2048;
     if (bx < 1) bx = 1;
     launch_k(fcwdm::pack_all_kernel, dim3((unsigned)bx, (unsigned)n_jobs), dim3(256), 0, (cudaStream_t)stream,
              (const fcwdm::PackJob*)jobs);

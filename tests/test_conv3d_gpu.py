@@ -243,3 +243,32 @@ def test_conv3d_fused_input_groupnorm(case):
     a = bf16_round(F.silu(F.group_norm(x, G, gamma, beta, 1e-5)))       # the kernel feeds bf16 operands to the MMA
     ref = F.conv3d(a, w, bias, padding=1) + cb[:, :, None, None, None] + res
     check(got, ref)
+
+
+def test_pack_all_matches_the_per_conv_packers():
+    """fcwdm_conv3d_pack_all (one launch re-packing every conv of a model, forward and data-gradient forms, staged
+    through shared memory) against the single-conv packing entry points, bit for bit, padding included."""
+    import torch
+    from fcwdm import native, ops
+    g = torch.Generator().manual_seed(3)
+    shapes = [(64, 64, 3), (64, 32, 3), (8, 64, 3), (128, 64, 3), (64, 192, 3), (256, 384, 3), (128, 64, 1), (64, 192, 1),
+              (24, 40, 3), (16, 8, 1)]
+    jobs, want, keep = [], [], []
+    for co, ci, k in shapes:
+        w = (torch.randn((co, ci, k, k, k), generator=g) * 0.1).cuda()
+        keep.append(w)
+        forms = [(co, ci, 0, w)]
+        if ci % 8 == 0:
+            forms.append((ci, co, 1, ops.conv3d_transpose_flip_weights(w)))
+        for O, I, transposed, w_form in forms:
+            pair = ops.conv3d_pair_supported(I, O, k)
+            ref = ops.conv3d_pair_pack_weights(w_form) if pair else ops.conv3d_pack_weights(w_form)
+            dst = torch.full_like(ref, float("nan"))
+            want.append((ref, dst, (co, ci, k, transposed, pair)))
+            jobs.append([w.data_ptr(), dst.data_ptr(), O, I, k ** 3, int(pair), transposed, ref.numel()])
+    table = torch.tensor(jobs, dtype=torch.int64).cuda()
+    with ops._on(table.device) as st:
+        native.call("fcwdm_conv3d_pack_all", ops._ptr(table), table.shape[0], max(j[7] for j in jobs), st)
+    torch.cuda.synchronize()
+    for ref, dst, tag in want:
+        assert torch.equal(dst.view(torch.int16), ref.view(torch.int16)), tag
