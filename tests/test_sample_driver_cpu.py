@@ -1,7 +1,6 @@
 """Host side of the sampling driver: the NIfTI-1 reader / writer against the published format,
 the BraTS case loader's item layout (bratsloader.py:9-109 of the reference) and the case bookkeeping."""
 import gzip
-import os
 import struct
 
 import numpy as np

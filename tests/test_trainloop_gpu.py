@@ -2,7 +2,6 @@
 configuration through the public surface scripts/train.py uses -- create_named_schedule_sampler, TrainLoop(...).run_loop()
 -- compared with the same steps written out by hand (training_losses + backward + FusedAdamW, what
 tests/test_train_gpu.py pins to the reference fixture), plus the checkpoint / resume cycle."""
-import os
 
 import numpy as np
 import pytest
