@@ -4,6 +4,7 @@
 // All HBM-bound elementwise / reduction passes on channels-last bf16 gradients with fp32 math; parameter
 // gradients are fp32 and ACCUMULATE into their destination (the caller zeroes them once per step), which is what
 // weight-tied ResBlocks (wunet.py:647-673) need.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace fcwdm {
@@ -535,10 +536,15 @@ static int gn_bwd_check(const char* fn, int64_t N, int64_t S, int64_t C, int64_t
     return FCWDM_OK;
 }
 
-static inline dim3 slab_grid(int64_t N, int64_t S, int64_t C, int per_thread) {
+// blocks_per_sm caps the grid: measured (tools/gnbwd_probe.py, 2 x 64 ch x 1 M voxels / 2 x 128 x 125 k) the two GroupNorm
+// backward passes want ONE resident wave (2 blocks per SM: 302 -> 286 us and 104 -> 83 us against a cap of 8), the
+// plain column sum wants more blocks in flight (56 us at 8 per SM, 98 us at 2).
+static inline dim3 slab_grid(int64_t N, int64_t S, int64_t C, int per_thread, int blocks_per_sm) {
     const int64_t vpb = kTrThreads / (C / 8);
     int64_t blocks = (S + vpb * per_thread - 1) / (vpb * per_thread);
-    const int64_t cap = (int64_t)num_sms() * 8 / (N > 8 ? 8 : N);
+    static const int env_per_sm = getenv("FCWDM_TR_BLOCKS_PER_SM") ? atoi(getenv("FCWDM_TR_BLOCKS_PER_SM")) : 0;
+    const int per_sm = env_per_sm > 0 ? env_per_sm : blocks_per_sm;
+    const int64_t cap = (int64_t)num_sms() * per_sm / (N > 8 ? 8 : N);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return dim3((unsigned)blocks, (unsigned)N);
@@ -564,7 +570,7 @@ extern "C" int fcwdm_groupnorm_bwd(const void* x, int64_t x_ld, const void* dy, 
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * N * C * kTrReplicas, st);
     FCWDM_REQUIRE(e == cudaSuccess, FCWDM_ERR_CUDA, "fcwdm_groupnorm_bwd: memset failed (%s)", cudaGetErrorString(e));
-    const dim3 grid = slab_grid(N, S, C, 4);
+    const dim3 grid = slab_grid(N, S, C, 4, 2);
     const dim3 blk((unsigned)((kTrThreads / (C / 8)) * (C / 8)));      // 256, or e.g. 240 for C = 192 / 384
     const size_t sm1 = (16 * kTrThreads + 4 * C) * sizeof(float), sm2 = 8 * C * sizeof(float);
     const __nv_bfloat16 *xp = (const __nv_bfloat16*)x, *dp = (const __nv_bfloat16*)dy, *ap = (const __nv_bfloat16*)acc;
@@ -590,7 +596,7 @@ extern "C" int fcwdm_colsum_cl(const void* x, int64_t ld, float* out_sample, int
     FCWDM_REQUIRE(C % 8 == 0 && C <= 2048 && ld >= C && ld % 8 == 0 && al16(x), FCWDM_ERR_UNSUPPORTED,
                   "fcwdm_colsum_cl: C must be a multiple of 8 (<= 2048), ld >= C, 16-byte aligned");
     if (N * S == 0) return FCWDM_OK;
-    launch_k(colsum_cl_kernel, slab_grid(N, S, C, 8), dim3((unsigned)((kTrThreads / (C / 8)) * (C / 8))), 8 * kTrThreads * sizeof(float),
+    launch_k(colsum_cl_kernel, slab_grid(N, S, C, 8, 8), dim3((unsigned)((kTrThreads / (C / 8)) * (C / 8))), 8 * kTrThreads * sizeof(float),
              (cudaStream_t)stream, (const __nv_bfloat16*)x, ld, out_sample, os_ld, out_total, S, (int)C);
     FCWDM_CHECK_LAUNCH("fcwdm_colsum_cl");
     return FCWDM_OK;
