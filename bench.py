@@ -361,8 +361,9 @@ def run_gpu(args):
             "metric": "sampled 224x224x160 volumes/sec", "value": value, "unit": "volumes/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD if MODEL["name"] == "wunet" else WORKLOAD.replace(
-                           "WavUNetModel CFG-W4 (1,2,2,4)", "plain UNetModel (run.sh: 1,2,2,4,4, resample_2d=False)"),
+            "config": {"workload": (WORKLOAD if MODEL["name"] == "wunet" else WORKLOAD.replace(
+                           "WavUNetModel CFG-W4 (1,2,2,4)", "plain UNetModel (run.sh: 1,2,2,4,4, resample_2d=False)")
+                                    ).replace("batch 1,", f"batch {args.batch},"),
                        "parallelism": f"volumes sharded over {world} GPU(s), no collective",
                        "l2": "per-step activations ~10 GB >> 126 MB L2 (no flush needed)", "T": T_STEPS, "volumes_per_step": args.batch,
                        "denoiser_gflop_per_step": flop_step / 1e9, "peaks": peaks["src"],
