@@ -141,13 +141,11 @@ def read(path, dtype=np.float64, return_header=False):
     return (out, h) if return_header else out
 
 
-def _quaternion_of(affine):
-    """(pixdim[0..3], quatern b,c,d) for an affine whose 3x3 part is a positive diagonal (identity rotation); None when
-    it has rotation or flips (then only the sform is meaningful and qform_code stays 0)."""
+def _is_positive_diagonal(affine):
+    """True when the 3x3 part is a positive diagonal (identity rotation): the qform quaternion is then (0, 0, 0) and
+    the offsets are the translation; with rotation or flips only the sform is written (qform_code stays 0)."""
     M = affine[:3, :3]
-    if np.count_nonzero(M - np.diag(np.diag(M))) or np.any(np.diag(M) <= 0):
-        return None
-    return (1.0, float(M[0, 0]), float(M[1, 1]), float(M[2, 2])), (0.0, 0.0, 0.0)
+    return not np.count_nonzero(M - np.diag(np.diag(M))) and bool(np.all(np.diag(M) > 0))
 
 
 def build_header(shape, dtype, affine=None, like=None):
@@ -168,7 +166,7 @@ def build_header(shape, dtype, affine=None, like=None):
     struct.pack_into("<2h", b, 70, _CODES[dtype], dtype.itemsize * 8)
     norms = np.sqrt((affine[:3, :3] ** 2).sum(axis=0))
     pixdim = [1.0] + [float(v) for v in norms] + [1.0] * 4
-    q = _quaternion_of(affine)
+    plain = _is_positive_diagonal(affine)
     qform_code = 0
     if from_like:
         pixdim = list(like.pixdim)
@@ -180,8 +178,8 @@ def build_header(shape, dtype, affine=None, like=None):
             qform_code = like.qform_code
             struct.pack_into("<3f", b, 256, *like.quatern)
             struct.pack_into("<3f", b, 268, *like.qoffset)
-    if q is not None and qform_code == 0:
-        struct.pack_into("<3f", b, 256, *q[1])
+    if plain and qform_code == 0:
+        struct.pack_into("<3f", b, 256, 0.0, 0.0, 0.0)
         struct.pack_into("<3f", b, 268, *(float(v) for v in affine[:3, 3]))
     struct.pack_into("<8f", b, 76, *pixdim)
     struct.pack_into("<2h", b, 252, qform_code, 2)                           # sform_code 2 = aligned

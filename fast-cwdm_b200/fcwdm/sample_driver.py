@@ -151,9 +151,10 @@ class SamplingDriver:
                     n += nifti.write(os.path.join(folder, "target.nii.gz"), target[0].numpy().T, np.eye(4),
                                      compresslevel=self.compresslevel)
             else:
-                folder = self.output_dir or os.path.dirname(case.files[conditions_for(case.contr)[0]])
                 if self.output_dir is not None:
                     folder = os.path.join(self.output_dir, case.subject)
+                else:                                       # next to the inputs, as sample_auto.py:77 does
+                    folder = os.path.dirname(case.files[conditions_for(case.contr)[0]])
                 os.makedirs(folder, exist_ok=True)
                 full = np.zeros(RAW_SHAPE[::-1], dtype=np.float32)        # pad back to 240 x 240 (sample_auto.py:143)
                 full[:, 8:-8, 8:-8] = result[0].numpy()
