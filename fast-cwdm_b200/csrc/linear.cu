@@ -5,7 +5,8 @@
 
 namespace fcwdm {
 
-__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int64_t N, int dim,
+template <typename T>      // int64 timesteps, or float ones (rescale_timesteps: t * 1000 / T, respace.py:128-132)
+__global__ void timestep_embedding_kernel(const T* __restrict__ t, float* __restrict__ out, int64_t N, int dim,
                                           float max_period) {
     pdl_prologue();
     const int half = dim / 2;
@@ -51,9 +52,21 @@ extern "C" int fcwdm_timestep_embedding(const int64_t* t, float* out, int64_t N,
     FCWDM_REQUIRE(N >= 0 && dim > 0 && max_period > 0.f, FCWDM_ERR_INVALID, "fcwdm_timestep_embedding: bad argument");
     if (N == 0) return FCWDM_OK;
     const int64_t total = N * dim;
-    launch_k(timestep_embedding_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, t, out, N, (int)dim,
-                                                                                                max_period);
+    launch_k(timestep_embedding_kernel<int64_t>, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, t, out, N,
+             (int)dim, max_period);
     FCWDM_CHECK_LAUNCH("fcwdm_timestep_embedding");
+    return FCWDM_OK;
+}
+
+extern "C" int fcwdm_timestep_embedding_f32(const float* t, float* out, int64_t N, int64_t dim, float max_period,
+                                            void* stream) {
+    FCWDM_REQUIRE(t && out, FCWDM_ERR_INVALID, "fcwdm_timestep_embedding_f32: null pointer");
+    FCWDM_REQUIRE(N >= 0 && dim > 0 && max_period > 0.f, FCWDM_ERR_INVALID, "fcwdm_timestep_embedding_f32: bad argument");
+    if (N == 0) return FCWDM_OK;
+    const int64_t total = N * dim;
+    launch_k(timestep_embedding_kernel<float>, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, t, out, N,
+             (int)dim, max_period);
+    FCWDM_CHECK_LAUNCH("fcwdm_timestep_embedding_f32");
     return FCWDM_OK;
 }
 

@@ -23,6 +23,12 @@ def _ld(c):
     return (c + 63) // 64 * 64
 
 
+def _timesteps(t):
+    """(N,) timesteps as the embedding kernel takes them: int64, or float32 when they are fractional (the model sees
+    t * 1000 / T with rescale_timesteps=True, gaussian_diffusion.py:417-420 / respace.py:128-132)."""
+    return t.float().contiguous() if t.is_floating_point() else t.to(torch.int64).contiguous()
+
+
 class _Packed:
     __slots__ = ("wp", "bias", "cin", "cout", "k", "pair")
 
@@ -265,7 +271,7 @@ class WavUNetEngine:
         return e2
 
     def forward_cl(self, x_cl, t, N, dims, out_ld=None):
-        """x_cl: (N*S, >= round_up(in_channels, 64)) bf16 channels-last; t: (N,) int64 CUDA.
+        """x_cl: (N*S, >= round_up(in_channels, 64)) bf16 channels-last; t: (N,) int64 (or float32) CUDA.
         Returns the (N*S, out_ld) bf16 channels-last model output.  Mirrors WavUNetModel.forward
         (reference wunet.py:734-795)."""
         from guided_diffusion.wunet import ResBlock, WaveletDownsample
@@ -329,15 +335,13 @@ class WavUNetEngine:
             raise FcwdmError("WavUNetModel.forward: input is on the CPU; the fcwdm denoiser has no CPU path")
         if x.dim() != 5 or x.shape[1] != m.in_channels:
             raise ValueError(f"expected input of shape (N, {m.in_channels}, D, H, W), got {tuple(x.shape)}")
-        if timesteps.is_floating_point():
-            raise NotImplementedError("fractional timesteps (rescale_timesteps=True) are not implemented")
         N, C, D, H, W = x.shape
         S = D * H * W
         with torch.cuda.device(x.device):
             x_cl = torch.zeros((N * S, _ld(C)), dtype=torch.bfloat16, device=x.device) if _ld(C) != C else \
                 torch.empty((N * S, C), dtype=torch.bfloat16, device=x.device)
             ops.planar_to_cl(x.float(), x_cl, C)
-            out_cl = self.forward_cl(x_cl, timesteps.to(torch.int64).contiguous(), N, (D, H, W))
+            out_cl = self.forward_cl(x_cl, _timesteps(timesteps), N, (D, H, W))
             out = torch.empty((N, m.out_channels, D, H, W), dtype=torch.float32, device=x.device)
             ops.cl_to_planar(out_cl, out, m.out_channels)
         return out.to(x.dtype) if x.dtype != torch.float32 else out

@@ -35,6 +35,7 @@ PROTOTYPES = {
     "fcwdm_groupnorm_apply": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64,
                                        _c_f, _c_int, _c_p]),
     "fcwdm_timestep_embedding": (_c_int, [_c_p, _c_p, _c_i64, _c_i64, _c_f, _c_p]),
+    "fcwdm_timestep_embedding_f32": (_c_int, [_c_p, _c_p, _c_i64, _c_i64, _c_f, _c_p]),
     "fcwdm_linear": (_c_int, [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_p]),
     "fcwdm_conv3d_packed_elems": (_c_i64, [_c_i64, _c_i64, _c_int]),
     "fcwdm_conv3d_pack_weights": (_c_int, [_c_p, _c_p, _c_i64, _c_i64, _c_int, _c_p]),

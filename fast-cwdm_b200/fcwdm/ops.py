@@ -204,8 +204,16 @@ def groupnorm_stats(x, stats, N, S, C, G):
 
 
 def timestep_embedding(t, out, dim, max_period=10000.0):
+    """t: (N,) int64, or float32 for fractional timesteps (rescale_timesteps=True)."""
+    if t.dtype == torch.int64:
+        name = "fcwdm_timestep_embedding"
+    elif t.dtype == torch.float32:
+        name = "fcwdm_timestep_embedding_f32"
+    else:
+        raise TypeError(f"timesteps must be int64 or float32, got {t.dtype}")
+    t = t.contiguous()
     with _on(t.device) as st:
-        native.call("fcwdm_timestep_embedding", _ptr(t), _ptr(out), t.shape[0], dim, float(max_period), st)
+        native.call(name, _ptr(t), _ptr(out), t.shape[0], dim, float(max_period), st)
 
 
 def linear(x, W, b, y, act_in=0, act_out=0):

@@ -18,7 +18,7 @@ operate on).  Weight-tied ResBlocks accumulate both uses into the same slice.
 import torch
 
 from . import ops
-from .engine import WavUNetEngine, _ld, _Packed
+from .engine import WavUNetEngine, _ld, _Packed, _timesteps
 from .native import FcwdmError
 
 
@@ -314,8 +314,6 @@ class WavUNetTrainEngine(WavUNetEngine):
             raise FcwdmError("WavUNetModel.forward: input is on the CPU; the fcwdm denoiser has no CPU path")
         if x.dim() != 5 or x.shape[1] != m.in_channels:
             raise ValueError(f"expected input of shape (N, {m.in_channels}, D, H, W), got {tuple(x.shape)}")
-        if timesteps.is_floating_point():
-            raise NotImplementedError("fractional timesteps (rescale_timesteps=True) are not implemented")
         N, C, D, H, W = x.shape
         dims = (D, H, W)
         levels = len(m.channel_mult)
@@ -333,7 +331,7 @@ class WavUNetTrainEngine(WavUNetEngine):
             S = D * H * W
             x_cl = torch.zeros((N * S, _ld(C)), dtype=torch.bfloat16, device=dev)
             ops.planar_to_cl(x.detach().float(), x_cl, C)
-            t = timesteps.to(torch.int64).contiguous()
+            t = _timesteps(timesteps)
 
             emb_all, d_emb_all = self._time_path_t(t, N, dev)
 
@@ -524,8 +522,6 @@ class UNetTrainEngine(WavUNetTrainEngine):
             raise FcwdmError("UNetModel.forward: input is on the CPU; the fcwdm denoiser has no CPU path")
         if x.dim() != 5 or x.shape[1] != m.in_channels:
             raise ValueError(f"expected input of shape (N, {m.in_channels}, D, H, W), got {tuple(x.shape)}")
-        if timesteps.is_floating_point():
-            raise NotImplementedError("fractional timesteps (rescale_timesteps=True) are not implemented")
         for mod in m.modules():
             if getattr(mod, "dropout", 0) and hasattr(mod, "in_layers"):
                 raise NotImplementedError("dropout > 0 in training is not implemented (run.sh ships dropout=0)")
@@ -539,7 +535,7 @@ class UNetTrainEngine(WavUNetTrainEngine):
             x_cl = torch.zeros((N * S, _ld(C)), dtype=torch.bfloat16, device=dev)
             ops.planar_to_cl(x.detach().float(), x_cl, C)
             self._x_in = x_cl
-            out_cl = self.forward_cl(x_cl, timesteps.to(torch.int64).contiguous(), N, (D, H, W))
+            out_cl = self.forward_cl(x_cl, _timesteps(timesteps), N, (D, H, W))
             self._out_cl = out_cl
             self._shape = (N, D, H, W)
             out = torch.empty((N, m.out_channels, D, H, W), dtype=torch.float32, device=dev)

@@ -146,6 +146,10 @@ int fcwdm_groupnorm_apply(const void* x, int64_t x_ld, void* y, int64_t y_ld, co
  * ---------------------------------------------------------------------------------------------------- */
 int fcwdm_timestep_embedding(const int64_t* t, float* out, int64_t N, int64_t dim, float max_period,
                              void* stream);
+/* Same for fractional timesteps: what the model sees with rescale_timesteps=True (t * 1000 / T as float,
+ * gaussian_diffusion.py:417-420, respace.py:128-132). */
+int fcwdm_timestep_embedding_f32(const float* t, float* out, int64_t N, int64_t dim, float max_period,
+                                 void* stream);
 int fcwdm_linear(const float* x, const float* W, const float* b, float* y, int64_t N, int64_t K, int64_t M,
                  int act_in, int act_out, void* stream);
 

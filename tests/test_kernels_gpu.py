@@ -119,6 +119,13 @@ def test_timestep_path():
     # |d cos(t*f)| <= t * ulp(f): the fp32 exp of the frequency may differ by 1 ulp between libms (t <= 999)
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=1e-4)
     np.testing.assert_allclose(out[:3].cpu().numpy(), ref[:3].numpy(), atol=2e-5)
+    # fractional timesteps (rescale_timesteps=True: the model sees t * 1000 / T as float32)
+    tf = torch.tensor([0.0, 0.5, 111.0, 333.3, 999.0], device="cuda")
+    ops.timestep_embedding(tf, out, 64)
+    reff = ow.timestep_embedding(tf.cpu(), 64)
+    np.testing.assert_allclose(out.cpu().numpy(), reff.numpy(), atol=1e-4)
+    with pytest.raises(TypeError):
+        ops.timestep_embedding(tf.double(), out, 64)
     g = torch.Generator().manual_seed(1)
     x = torch.randn(5, 64, generator=g)
     W = torch.randn(256, 64, generator=g) * 0.1

@@ -46,6 +46,31 @@ def test_small_model_matches_reference_fixture(golden):
     assert rel <= 3e-2 and mx <= 6e-2 * float(ref.abs().max()) and psnr(y.cpu(), ref) >= 40.0
 
 
+def test_fractional_timesteps_against_oracle():
+    """rescale_timesteps=True hands the model float timesteps t * 1000 / T (gaussian_diffusion.py:417-420,
+    respace.py:128-132): same denoiser, same tolerance, against the oracle with the same float t; and through the
+    public diffusion API (SpacedDiffusion with rescaling goes through the per-step path)."""
+    from guided_diffusion.script_util import create_gaussian_diffusion
+    m, sd = small_model()
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 32, 8, 8, 8, generator=g)
+    t = torch.tensor([3, 7]).float() * (1000.0 / 10)
+    with torch.no_grad():
+        y = m(x.cuda(), t.cuda()).cpu()
+        ref = ow.wunet_forward(sd, x, t, model_channels=SMALL_CFG["model_channels"], channel_mult=SMALL_CFG["channel_mult"],
+                               num_res_blocks=SMALL_CFG["num_res_blocks"], num_groups=SMALL_CFG["num_groups"])
+        y_int = m(x.cuda(), torch.tensor([3, 7]).cuda()).cpu()
+    rel = float((y - ref).norm() / ref.norm())
+    assert rel <= 3e-2 and psnr(y, ref) >= 40.0, rel
+    assert float((y - y_int).abs().max()) > 1e-3                  # t = 300 is not t = 3
+    d = create_gaussian_diffusion(steps=1000, timestep_respacing="10", predict_xstart=True, rescale_timesteps=True, mode="i2i")
+    noise = torch.randn(1, 8, 8, 8, 8, generator=g).cuda()
+    cond = torch.rand(1, 24, 8, 8, 8, generator=g).cuda()
+    torch.manual_seed(2)
+    out = d.p_sample_loop(m, (1, 8, 8, 8, 8), noise=noise, cond=cond, progress=False)
+    assert out.shape == (1, 8, 8, 8, 8) and bool(torch.isfinite(out).all())
+
+
 def test_weight_update_is_picked_up():
     m, sd = small_model()
     x = torch.randn(1, 32, 8, 8, 8, device="cuda")
