@@ -224,6 +224,8 @@ class WavUNetEngine:
         dev = x.device
         cin, cout = blk.channels, blk.out_channels
         emb_out = self._emb_out(blk, emb)
+        ssn = getattr(blk, "use_scale_shift_norm", False)
+        emb_add = None if ssn else emb_out              # scale-shift norm: emb_out modulates the second GroupNorm instead
         gn1, conv1 = blk.in_layers[0], blk.in_layers[2]
         skip_out = skip
         if blk.down:
@@ -234,7 +236,7 @@ class WavUNetEngine:
             hi = torch.empty((7, N * s2, _ld(cout)), dtype=torch.bfloat16, device=dev) if _ld(cout) == cout else \
                 torch.zeros((7, N * s2, _ld(cout)), dtype=torch.bfloat16, device=dev)
             # h, hSkip = Downsample(h): LLL/3 (+ emb, :262) and the 7 high bands (:118-121, :240)
-            ops.dwt3d_cl(h_full, (N,) + tuple(dims), cout, h, hi, lll_bias=emb_out, lll_scale=1.0 / 3.0)
+            ops.dwt3d_cl(h_full, (N,) + tuple(dims), cout, h, hi, lll_bias=emb_add, lll_scale=1.0 / 3.0)
             xs = self._buf(N * s2, cin, dev)
             ops.dwt3d_cl(x, (N,) + tuple(dims), cin, xs, None, lll_scale=1.0 / 3.0)      # x_upd: LLL/3 only (:241)
             x, dims, S, skip_out = xs, d2, s2, hi
@@ -245,18 +247,41 @@ class WavUNetEngine:
             d2 = (dims[0] * 2, dims[1] * 2, dims[2] * 2)
             s2 = d2[0] * d2[1] * d2[2]
             h = self._buf(N * s2, cout, dev)
-            ops.idwt3d_cl(h_low, skip, (N,) + d2, cout, h, bias=emb_out, lll_scale=3.0)   # IDWT(3h, skip) + emb
+            ops.idwt3d_cl(h_low, skip, (N,) + d2, cout, h, bias=emb_add, lll_scale=3.0)   # IDWT(3h, skip) + emb
             xu = self._buf(N * s2, cin, dev)
             ops.idwt3d_cl(x, skip, (N,) + d2, cin, xu, bias=None, lll_scale=3.0)          # IDWT(3x, skip)
             x, dims, S, skip_out = xu, d2, s2, None
         else:
-            h = self._gn_silu_conv(gn1, x, conv1, N, dims, chan_bias=emb_out,             # conv + emb (:262)
+            h = self._gn_silu_conv(gn1, x, conv1, N, dims, chan_bias=emb_add,             # conv + emb (:262)
                                    stats_groups=blk.out_layers[0].num_groups)
         if isinstance(blk.skip_connection, torch.nn.Conv3d):
             x = self._conv3d(blk.skip_connection, x, N, dims)
-        out = self._gn_silu_conv(blk.out_layers[0], h, blk.out_layers[3], N, dims, residual=x,   # skip(x) + h (:266)
-                                 stats_groups=self.model.num_groups)
+        if ssn:
+            a = self._gn_silu_ssn(blk.out_layers[0], h, emb_out, N, S)
+            out = self._conv3d(blk.out_layers[3], a, N, dims, residual=x, stats_groups=self.model.num_groups)
+        else:
+            out = self._gn_silu_conv(blk.out_layers[0], h, blk.out_layers[3], N, dims, residual=x,   # skip(x) + h (:266)
+                                     stats_groups=self.model.num_groups)
         return out, skip_out, dims
+
+    def _gn_silu_ssn(self, gn, x, emb_out, N, S):
+        """SiLU(GroupNorm(x) * (1 + scale) + shift) with (scale, shift) = chunk(emb_out, 2) per sample (reference
+        wunet.py:256-260): the per-sample modulation folds into the affine parameters, gamma' = gamma * (1 + scale),
+        beta' = beta * (1 + scale) + shift, so each sample is one fused GroupNorm+SiLU launch with its own (gamma', beta')."""
+        C = gn.num_channels
+        if emb_out.shape[1] != 2 * C:
+            raise FcwdmError(f"scale-shift norm: emb_layers must produce 2 x {C} values, got {emb_out.shape[1]}")
+        y = self._buf(N * S, C, x.device)
+        stats, have = self._take_stats(gn, x, N)
+        if not have:
+            ops.groupnorm_stats(x, stats, N, S, C, gn.num_groups)
+        one_plus = 1.0 + emb_out[:, :C].float()
+        gamma = (self._p32(gn.weight)[None] * one_plus).contiguous()
+        beta = (self._p32(gn.bias)[None] * one_plus + emb_out[:, C:].float()).contiguous()
+        for n in range(N):
+            ops.groupnorm_silu(x[n * S:(n + 1) * S], y[n * S:(n + 1) * S], stats[n:n + 1], gamma[n], beta[n], 1, S, C,
+                               gn.num_groups, gn.eps, True, have_stats=True)
+        return y
 
     # ------------------------------------------------------------------ whole network
     def time_embedding(self, t):

@@ -235,6 +235,9 @@ class WavUNetTrainEngine(WavUNetEngine):
         cin, cout = blk.channels, blk.out_channels
         if blk.dropout:
             raise NotImplementedError("dropout > 0 in training is not implemented (run.sh ships dropout=0)")
+        if getattr(blk, "use_scale_shift_norm", False):
+            raise NotImplementedError("training with use_scale_shift_norm=True is not implemented (inference is; run.sh "
+                                      "trains with False)")
         emb = self._emb_slice(blk, emb_all, d_emb_all)
         gn1, conv1 = blk.in_layers[0], blk.in_layers[2]
         skip_out = skip
@@ -525,6 +528,9 @@ class UNetTrainEngine(WavUNetTrainEngine):
         for mod in m.modules():
             if getattr(mod, "dropout", 0) and hasattr(mod, "in_layers"):
                 raise NotImplementedError("dropout > 0 in training is not implemented (run.sh ships dropout=0)")
+            if getattr(mod, "use_scale_shift_norm", False) and hasattr(mod, "in_layers"):
+                raise NotImplementedError("training with use_scale_shift_norm=True is not implemented (inference is; "
+                                          "run.sh trains with False)")
         N, C, D, H, W = x.shape
         dev = x.device
         with torch.cuda.device(dev):

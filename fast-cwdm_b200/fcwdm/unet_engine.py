@@ -38,6 +38,8 @@ class UNetEngine(WavUNetEngine):
         S = dims[0] * dims[1] * dims[2]
         cin = blk.channels
         emb_out = self._emb_out(blk, emb)
+        ssn = getattr(blk, "use_scale_shift_norm", False)
+        emb_add = None if ssn else emb_out              # scale-shift norm: emb_out modulates the second GroupNorm instead
         gn1, conv1 = blk.in_layers[0], blk.in_layers[2]
         g2 = blk.out_layers[0].num_groups
         if blk.updown:
@@ -46,13 +48,17 @@ class UNetEngine(WavUNetEngine):
             a, d2 = self._resample(a, N, dims, cin, blk.up, depth)             # h = h_upd(h)              (:289)
             x, _ = self._resample(x, N, dims, cin, blk.up, depth)              # x = x_upd(x)              (:290)
             dims = d2
-            h = self._conv3d(conv1, a, N, dims, chan_bias=emb_out, stats_groups=g2)   # in_conv(h) + emb_out (:291,:308)
+            h = self._conv3d(conv1, a, N, dims, chan_bias=emb_add, stats_groups=g2)   # in_conv(h) + emb_out (:291,:308)
         else:
-            h = self._gn_silu_conv(gn1, x, conv1, N, dims, chan_bias=emb_out, stats_groups=g2)
+            h = self._gn_silu_conv(gn1, x, conv1, N, dims, chan_bias=emb_add, stats_groups=g2)
         if isinstance(blk.skip_connection, torch.nn.Conv3d):
             x = self._conv3d(blk.skip_connection, x, N, dims)
-        res = self._gn_silu_conv(blk.out_layers[0], h, blk.out_layers[3], N, dims, residual=x,   # skip(x) + h (:311)
-                                 stats_groups=self.model.num_groups, out=out)
+        if ssn:                                                                # out_norm(h) * (1 + scale) + shift (:301-305)
+            a2 = self._gn_silu_ssn(blk.out_layers[0], h, emb_out, N, dims[0] * dims[1] * dims[2])
+            res = self._conv3d(blk.out_layers[3], a2, N, dims, residual=x, stats_groups=self.model.num_groups, out=out)
+        else:
+            res = self._gn_silu_conv(blk.out_layers[0], h, blk.out_layers[3], N, dims, residual=x,   # skip(x) + h (:311)
+                                     stats_groups=self.model.num_groups, out=out)
         return res, dims
 
     def _gn_silu_conv(self, gn, x, mod, N, dims, **kw):

@@ -10,8 +10,8 @@ embedding and residual in the epilogue), fused GroupNorm+SiLU, average-pool / ne
 skip concatenation (unet.py:796) without a copy -- producers write straight into column slices of the concat buffer.
 
 Supported flag set = what run.sh ships: dims=3, resblock_updown=True, no attention (attention_resolutions="",
-bottleneck_attention=False), use_scale_shift_norm=False, additive_skips=False, class_cond=False; resample_2d either
-way.  Anything else raises NotImplementedError at construction.  Sampling and training (autograd) are both served.
+bottleneck_attention=False), additive_skips=False, class_cond=False; resample_2d either way; use_scale_shift_norm
+either way for sampling (False for training).  Anything else raises NotImplementedError at construction.  Sampling and training (autograd) are both served.
 """
 import torch as th
 import torch.nn as nn
@@ -63,8 +63,6 @@ class ResBlock(TimestepBlock):
     def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=False, use_scale_shift_norm=False,
                  dims=2, use_checkpoint=False, up=False, down=False, num_groups=32, resample_2d=True):
         super().__init__()
-        if use_scale_shift_norm:
-            raise NotImplementedError("use_scale_shift_norm=True is not implemented (run.sh:116 ships False)")
         if dims != 3:
             raise NotImplementedError("only dims=3 is implemented")
         self.channels = channels
@@ -93,7 +91,8 @@ class ResBlock(TimestepBlock):
             self.x_upd = Downsample(channels, False, dims, resample_2d=resample_2d)
         else:
             self.h_upd = self.x_upd = nn.Identity()
-        self.emb_layers = nn.Sequential(nn.SiLU(), linear(emb_channels, self.out_channels))
+        # use_scale_shift_norm: emb_out = (scale, shift), h = out_norm(h) * (1 + scale) + shift (reference unet.py:301-305)
+        self.emb_layers = nn.Sequential(nn.SiLU(), linear(emb_channels, (2 if use_scale_shift_norm else 1) * self.out_channels))
         self.out_layers = nn.Sequential(
             normalization(self.out_channels, self.num_groups),
             nn.SiLU(),

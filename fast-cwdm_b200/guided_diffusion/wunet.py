@@ -9,8 +9,8 @@ as a sequence of hand-written sm_100a kernels on channels-last bf16 activations 
 fused GroupNorm+SiLU, one-pass Haar DWT/IDWT with the /3, x3 and timestep-embedding adds folded in).
 
 Supported flag set = the only one under which the reference model itself runs:
-dims=3, use_freq=True, resblock_updown=True, additive_skips=False, no attention, use_scale_shift_norm=False,
-progressive_input='residual'.  Anything else raises NotImplementedError at construction instead of failing
+dims=3, use_freq=True, resblock_updown=True, additive_skips=False, no attention, progressive_input='residual';
+use_scale_shift_norm either way for inference (False, what run.sh ships, for training).  Anything else raises NotImplementedError at construction instead of failing
 deep inside forward as the reference does.
 """
 from abc import abstractmethod
@@ -99,8 +99,6 @@ class ResBlock(TimestepBlock):
     def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=True, use_scale_shift_norm=False,
                  dims=2, use_checkpoint=False, up=False, down=False, num_groups=32, resample_2d=True, use_freq=False):
         super().__init__()
-        if use_scale_shift_norm:
-            raise NotImplementedError("use_scale_shift_norm=True is not implemented (run.sh:126 ships False)")
         if dims != 3:
             raise NotImplementedError("only dims=3 is implemented")
         self.channels = channels
@@ -129,7 +127,8 @@ class ResBlock(TimestepBlock):
             self.x_upd = Downsample(channels, False, dims, resample_2d=resample_2d, use_freq=self.use_freq)
         else:
             self.h_upd = self.x_upd = nn.Identity()
-        self.emb_layers = nn.Sequential(nn.SiLU(), linear(emb_channels, self.out_channels))
+        # use_scale_shift_norm: emb_out = (scale, shift), h = out_norm(h) * (1 + scale) + shift (reference wunet.py:256-260)
+        self.emb_layers = nn.Sequential(nn.SiLU(), linear(emb_channels, (2 if use_scale_shift_norm else 1) * self.out_channels))
         self.out_layers = nn.Sequential(
             normalization(self.out_channels, self.num_groups),
             nn.SiLU(),

@@ -233,3 +233,38 @@ def test_volume_stream_matches_direct_synthesis():
         assert torch.isfinite(out).all()
         # same kernels, same inputs: only the GroupNorm statistics' atomic summation order differs run to run
         assert float((out - ref).abs().max()) <= 5e-2 and float((out - ref).norm() / ref.norm().clamp_min(1e-6)) <= 1e-2
+
+
+@pytest.mark.parametrize("which", ["wunet", "unet"])
+def test_scale_shift_norm_matches_reference_fixture(golden, which):
+    """use_scale_shift_norm=True (the default of the reference's model_and_diffusion_defaults; run.sh passes False):
+    out_norm(h) * (1 + scale) + shift with (scale, shift) = chunk(emb_out, 2) (wunet.py:256-260, unet.py:301-305), against
+    a forward of the unmodified reference (oracle/make_golden_ssn.py).  Inference only: training refuses the flag."""
+    from oracle.make_golden_unet import UNET_SMALL_CFG
+    if which == "wunet":
+        from guided_diffusion.wunet import WavUNetModel as Model
+        cfg, fixture, tie = dict(SMALL_CFG, use_scale_shift_norm=True), "wunet_small_ssn", True
+    else:
+        from guided_diffusion.unet import UNetModel as Model
+        cfg, fixture, tie = dict(UNET_SMALL_CFG, use_scale_shift_norm=True), "unet_small_ssn", False
+    g = golden(fixture)
+    m = Model(**cfg)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert sorted(shapes) == [str(k) for k in g["keys"]]
+    assert [",".join(map(str, shapes[k])) for k in sorted(shapes)] == [str(v) for v in g["shapes"]]
+    sd = ow.seeded_state_dict(shapes, seed=0)
+    if tie:
+        sd = ow.tie_output_blocks(sd, len(cfg["channel_mult"]))
+    m.load_state_dict(sd, strict=True)
+    m.to("cuda")
+    m.eval()
+    with torch.no_grad():
+        y = m(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda()).cpu()
+    ref = torch.from_numpy(g["y"])
+    rel = float((y - ref).norm() / ref.norm())
+    print(f"{which} scale-shift norm: rel-L2 {rel:.3e} PSNR {psnr(y, ref):.1f} dB")
+    assert rel <= 3e-2 and psnr(y, ref) >= 40.0
+    m.train()
+    x = torch.from_numpy(g["x"]).cuda()
+    with pytest.raises(NotImplementedError):
+        m(x, torch.from_numpy(g["t"]).cuda())
