@@ -70,8 +70,10 @@ def test_unsupported_flags_fail_at_construction():
                 attention_resolutions=(), channel_mult=(1, 2), dims=3, bottleneck_attention=False,
                 resblock_updown=True, use_freq=True)
     WavUNetModel(**base)
+    ssn = WavUNetModel(**dict(base, use_scale_shift_norm=True))       # served (inference): emb_layers produce (scale, shift)
+    assert ssn.input_blocks[1][0].emb_layers[1].out_features == 2 * ssn.input_blocks[1][0].out_channels
     for bad in (dict(dims=2), dict(use_freq=False), dict(resblock_updown=False), dict(additive_skips=True),
-                dict(bottleneck_attention=True), dict(attention_resolutions=(2,)), dict(use_scale_shift_norm=True)):
+                dict(bottleneck_attention=True), dict(attention_resolutions=(2,))):
         with pytest.raises(NotImplementedError):
             WavUNetModel(**{**base, **bad})
 
