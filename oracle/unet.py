@@ -5,7 +5,7 @@ use_scale_shift_norm=False, additive_skips=False.  Weights come from a plain sta
 import torch
 import torch.nn.functional as F
 
-from .wunet import _conv, _gn_silu, timestep_embedding
+from .wunet import _conv, _emb_and_out_layers, _gn_silu, timestep_embedding
 
 
 def _resample(x, up, resample_2d):
@@ -27,8 +27,7 @@ def _resblock(sd, p, x, emb, groups, up=False, down=False, resample_2d=False):
     else:
         h = _conv(sd, p + "in_layers.2", _gn_silu(sd, p + "in_layers.0", x, groups), 1)  # :293
     emb_out = F.linear(F.silu(emb), sd[p + "emb_layers.1.weight"], sd[p + "emb_layers.1.bias"])   # :295
-    h = h + emb_out[:, :, None, None, None]                                             # :308
-    h = _conv(sd, p + "out_layers.3", _gn_silu(sd, p + "out_layers.0", h, groups), 1)   # :309
+    h = _emb_and_out_layers(sd, p, h, emb_out, groups)                                  # :297-309
     if (p + "skip_connection.weight") in sd:
         w = sd[p + "skip_connection.weight"]
         x = F.conv3d(x, w, sd[p + "skip_connection.bias"], padding=w.shape[-1] // 2)

@@ -79,6 +79,20 @@ def _conv(sd, p, x, pad):
     return F.conv3d(x, sd[p + ".weight"], sd[p + ".bias"], padding=pad)
 
 
+def _emb_and_out_layers(sd, p, h, emb_out, groups):
+    """The tail both U-Nets' ResBlocks share (wunet.py:252-263, unet.py:297-309): h + emb_out then out_layers, or --
+    use_scale_shift_norm, recognised by emb_layers producing 2 x C values -- out_norm(h) * (1 + scale) + shift with
+    (scale, shift) = chunk(emb_out, 2), then SiLU and the conv."""
+    C = sd[p + "out_layers.0.weight"].shape[0]
+    if emb_out.shape[1] == 2 * C:
+        scale = emb_out[:, :C, None, None, None]
+        shift = emb_out[:, C:, None, None, None]
+        hn = F.group_norm(h.float(), groups, sd[p + "out_layers.0.weight"], sd[p + "out_layers.0.bias"], 1e-5)
+        return _conv(sd, p + "out_layers.3", F.silu(hn * (1 + scale) + shift), 1)
+    h = h + emb_out[:, :, None, None, None]
+    return _conv(sd, p + "out_layers.3", _gn_silu(sd, p + "out_layers.0", h, groups), 1)
+
+
 def _resblock(sd, p, x, skip, emb, groups, up=False, down=False):
     """ResBlock.forward (:223-269).  ``x`` tensor, ``skip`` = 7-tuple of bands or None.
     Returns (out, hSkip)."""
@@ -93,8 +107,7 @@ def _resblock(sd, p, x, skip, emb, groups, up=False, down=False):
         x = _idwt(3.0 * x, *skip)
         hskip = None
     emb_out = F.linear(F.silu(emb), sd[p + "emb_layers.1.weight"], sd[p + "emb_layers.1.bias"])   # :250
-    h = h + emb_out[:, :, None, None, None]                                                # :252-262
-    h = _conv(sd, p + "out_layers.3", _gn_silu(sd, p + "out_layers.0", h, groups), 1)      # :263 (dropout p=0)
+    h = _emb_and_out_layers(sd, p, h, emb_out, groups)                                     # :252-263 (dropout p=0)
     if (p + "skip_connection.weight") in sd:                                               # :217-220
         x = _conv(sd, p + "skip_connection", x, 0)
     return x + h, hskip                                                                    # :266-267

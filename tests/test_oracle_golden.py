@@ -213,3 +213,18 @@ def test_preprocess(golden):
     assert out.shape == (1, 32, 28, 32) and out.dtype == np.float32
     np.testing.assert_array_equal(out[0, :, :, :23], g["vol_out"][4:-4, 4:-4].astype(np.float32))
     assert float(np.abs(out[..., 23:]).max()) == 0.0
+
+
+def test_scale_shift_norm_small(golden):
+    """use_scale_shift_norm=True (wunet.py:256-260, unet.py:301-305): both oracle U-Nets against forwards of the
+    unmodified reference (oracle/make_golden_ssn.py)."""
+    from oracle import unet as ou
+    for name, forward, mult, tie in (("wunet_small_ssn", ow.wunet_forward, (1, 2), True),
+                                     ("unet_small_ssn", ou.unet_forward, (1, 2, 2), False)):
+        g = golden(name)
+        shapes = {str(k): tuple(int(v) for v in str(s).split(",")) for k, s in zip(g["keys"], g["shapes"])}
+        sd = ow.seeded_state_dict(shapes, seed=0)
+        if tie:
+            sd = ow.tie_output_blocks(sd, len(mult))
+        y = forward(sd, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), model_channels=32, channel_mult=mult)
+        assert np.abs(y.numpy() - g["y"]).max() < 5e-5 * max(1.0, np.abs(g["y"]).max()), name
