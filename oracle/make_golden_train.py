@@ -76,7 +76,7 @@ def one_fixture(ref, model, sd_keys_tied, out_name):
 
 def main():
     import importlib
-    which = sys.argv[1:] or ["wunet", "unet"]
+    which = sys.argv[1:] or ["wunet", "unet", "wunet_ssn"]
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     with reference_modules() as ref:
         if "wunet" in which:
@@ -85,6 +85,13 @@ def main():
             sd = owunet.tie_output_blocks(owunet.seeded_state_dict(shapes, seed=0), len(SMALL_CFG["channel_mult"]))
             model.load_state_dict(sd, strict=True)
             one_fixture(ref, model, sd, "train_small.npz")
+        if "wunet_ssn" in which:                               # use_scale_shift_norm=True (wunet.py:256-260)
+            cfg = dict(SMALL_CFG, use_scale_shift_norm=True)
+            model = ref.wunet.WavUNetModel(**cfg)
+            shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+            sd = owunet.tie_output_blocks(owunet.seeded_state_dict(shapes, seed=0), len(cfg["channel_mult"]))
+            model.load_state_dict(sd, strict=True)
+            one_fixture(ref, model, sd, "train_small_ssn.npz")
         if "unet" in which:
             from oracle.make_golden_unet import UNET_SMALL_CFG
             unet = importlib.import_module("guided_diffusion.unet")

@@ -1,6 +1,7 @@
 """Pins the oracle (oracle/*.py) against fixtures produced by the unmodified reference
 (oracle/make_golden.py).  CPU only."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import diffusion as od
@@ -107,8 +108,8 @@ def test_sample_postprocess(golden):
     np.testing.assert_allclose(out.numpy(), g["post_out"], atol=2e-6)
 
 
-def _small_sd(golden):
-    g = golden("wunet_small")
+def _small_sd(golden, fixture="wunet_small"):
+    g = golden(fixture)
     shapes = {str(k): tuple(int(v) for v in str(s).split(",")) for k, s in zip(g["keys"], g["shapes"])}
     return ow.tie_output_blocks(ow.seeded_state_dict(shapes, seed=0), len(SMALL_CFG["channel_mult"]))
 
@@ -135,11 +136,13 @@ def test_loop_small(golden):
         np.testing.assert_allclose(img.numpy(), g["samples"][k], atol=2e-4)
 
 
-def test_training_step_small(golden):
-    """Loss, every parameter gradient and the AdamW update of one reference training step (train_small.npz)."""
+@pytest.mark.parametrize("fixture,weights", [("train_small", "wunet_small"), ("train_small_ssn", "wunet_small_ssn")])
+def test_training_step_small(golden, fixture, weights):
+    """Loss, every parameter gradient and the AdamW update of one reference training step (train_small.npz; the
+    _ssn pair is the same step with use_scale_shift_norm=True)."""
     from oracle import train as otr
-    g = golden("train_small")
-    sd = _small_sd(golden)
+    g = golden(fixture)
+    sd = _small_sd(golden, weights)
     tab, m10 = _tab10()
     batch = {k: torch.from_numpy(g["batch_" + k]) for k in ("t1n", "t1c", "t2w", "t2f")}
     loss, mse, out, grads = otr.training_step_grads(sd, tab, batch, torch.from_numpy(g["t"]), torch.from_numpy(g["noise"]),
