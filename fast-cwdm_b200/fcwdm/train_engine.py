@@ -235,10 +235,9 @@ class WavUNetTrainEngine(WavUNetEngine):
         cin, cout = blk.channels, blk.out_channels
         if blk.dropout:
             raise NotImplementedError("dropout > 0 in training is not implemented (run.sh ships dropout=0)")
-        if getattr(blk, "use_scale_shift_norm", False):
-            raise NotImplementedError("training with use_scale_shift_norm=True is not implemented (inference is; run.sh "
-                                      "trains with False)")
-        emb = self._emb_slice(blk, emb_all, d_emb_all)
+        ssn = getattr(blk, "use_scale_shift_norm", False)
+        emb_full = self._emb_slice(blk, emb_all, d_emb_all)
+        emb = None if ssn else emb_full                 # scale-shift norm: emb_out modulates the second GroupNorm instead
         gn1, conv1 = blk.in_layers[0], blk.in_layers[2]
         skip_out = skip
         d4 = (N,) + tuple(dims)
@@ -267,9 +266,59 @@ class WavUNetTrainEngine(WavUNetEngine):
             h = self._gn_silu_conv(gn1, x, conv1, N, dims, emb=emb, stats_groups=blk.out_layers[0].num_groups)
         if isinstance(blk.skip_connection, torch.nn.Conv3d):
             x = self._conv3d_t(blk.skip_connection, x, N, dims)
-        out = self._gn_silu_conv(blk.out_layers[0], h, blk.out_layers[3], N, dims, residual=x,
-                                 stats_groups=self.model.num_groups)
+        if ssn:
+            a = self._gn_silu_ssn_t(blk.out_layers[0], h, emb_full, N, dims[0] * dims[1] * dims[2])
+            out = self._conv3d_t(blk.out_layers[3], a, N, dims, residual=x, stats_groups=self.model.num_groups)
+        else:
+            out = self._gn_silu_conv(blk.out_layers[0], h, blk.out_layers[3], N, dims, residual=x,
+                                     stats_groups=self.model.num_groups)
         return out, skip_out, dims
+
+    def _gn_silu_ssn_t(self, gn, x, emb, N, S):
+        """Taped SiLU(GroupNorm(x) * (1 + scale) + shift), (scale, shift) = chunk(emb_out, 2) (reference wunet.py:256-260).
+        Forward: per sample, the fused GroupNorm+SiLU with gamma'_n = gamma (1 + scale_n), beta'_n = beta (1 + scale_n)
+        + shift_n.  Backward: the ordinary GroupNorm backward per sample gives dx and (dgamma'_n, dbeta'_n); then
+        dgamma = sum_n dgamma'_n (1 + scale_n), dbeta = sum_n dbeta'_n (1 + scale_n),
+        dscale_n = dgamma'_n gamma + dbeta'_n beta, dshift_n = dbeta'_n (into the timestep-embedding gradient)."""
+        C = gn.num_channels
+        d_emb_all, off, width, emb_out = emb
+        if width != 2 * C:
+            raise FcwdmError(f"scale-shift norm: emb_layers must produce 2 x {C} values, got {width}")
+        y = self._buf(N * S, C, x.device)
+        stats, have = self._take_stats(gn, x, N)
+        if not have:
+            ops.groupnorm_stats(x, stats, N, S, C, gn.num_groups)
+        gam, bet = self._p32(gn.weight), self._p32(gn.bias)
+        one_plus = (1.0 + emb_out[:, :C].float()).contiguous()
+        gamma_n = (gam[None] * one_plus).contiguous()
+        beta_n = (bet[None] * one_plus + emb_out[:, C:].float()).contiguous()
+        for n in range(N):
+            ops.groupnorm_silu(x[n * S:(n + 1) * S], y[n * S:(n + 1) * S], stats[n:n + 1], gamma_n[n], beta_n[n], 1, S, C,
+                               gn.num_groups, gn.eps, True, have_stats=True)
+        self._keep.append((x, y))
+        self._count(gn.weight, gn.bias)
+
+        def bwd():
+            dy = self._take(y)
+            if dy is None:
+                return
+            dx = self._buf(N * S, C, x.device)
+            acc = self._partial(x)
+            dgp = torch.zeros((N, C), dtype=torch.float32, device=x.device)
+            dbp = torch.zeros((N, C), dtype=torch.float32, device=x.device)
+            for n in range(N):
+                rows = slice(n * S, (n + 1) * S)
+                ops.groupnorm_bwd(x[rows], dy[rows], stats[n:n + 1], gamma_n[n], beta_n[n], dx[rows], dgp[n], dbp[n], 1, S, C,
+                                  gn.num_groups, gn.eps, True, acc=acc[rows] if acc is not None else None)
+            self._gp(gn.weight).add_((dgp * one_plus).sum(dim=0))
+            self._gp(gn.bias).add_((dbp * one_plus).sum(dim=0))
+            d_emb_all[:, off:off + C] += dgp * gam[None] + dbp * bet[None]
+            d_emb_all[:, off + C:off + 2 * C] += dbp
+            self._set(x, dx)
+            self._param_done(gn.weight, gn.bias)
+
+        self._tape.append(bwd)
+        return y
 
     def _time_path_t(self, t, N, dev):
         """Timestep path (wunet.py:472-475,736 / unet.py:777; ResBlock emb_layers) with pre-activations kept and the

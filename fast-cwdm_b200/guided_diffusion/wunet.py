@@ -10,7 +10,7 @@ fused GroupNorm+SiLU, one-pass Haar DWT/IDWT with the /3, x3 and timestep-embedd
 
 Supported flag set = the only one under which the reference model itself runs:
 dims=3, use_freq=True, resblock_updown=True, additive_skips=False, no attention, progressive_input='residual';
-use_scale_shift_norm either way for inference (False, what run.sh ships, for training).  Anything else raises NotImplementedError at construction instead of failing
+use_scale_shift_norm either way (run.sh ships False).  Anything else raises NotImplementedError at construction instead of failing
 deep inside forward as the reference does.
 """
 from abc import abstractmethod

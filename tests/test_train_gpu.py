@@ -61,10 +61,12 @@ def compare_grads(named_got, ref_of, ref_norms, label, rel_tol=8e-2):
     assert total <= 4e-2, (label, total)
 
 
-def test_training_step_matches_reference_fixture(golden):
+@pytest.mark.parametrize("fixture,ssn", [("train_small", False), ("train_small_ssn", True)])
+def test_training_step_matches_reference_fixture(golden, fixture, ssn):
+    """ssn: the same step with use_scale_shift_norm=True (out_norm(h) * (1 + scale) + shift, wunet.py:256-260)."""
     from guided_diffusion.script_util import create_gaussian_diffusion
-    g = golden("train_small")
-    model, _ = seeded_model(SMALL_CFG)
+    g = golden(fixture)
+    model, _ = seeded_model(dict(SMALL_CFG, use_scale_shift_norm=ssn))
     d10 = create_gaussian_diffusion(steps=10, predict_xstart=True, sample_schedule="sampled", mode="i2i")
     batch = {k: torch.from_numpy(g["batch_" + k]) for k in ("t1n", "t1c", "t2w", "t2f")}
     loss, terms, mo = run_training_losses(d10, model, batch, torch.from_numpy(g["t"]), torch.from_numpy(g["noise"]))
