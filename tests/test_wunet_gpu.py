@@ -273,3 +273,27 @@ def test_scale_shift_norm_matches_reference_fixture(golden, which):
         out = m(x, torch.from_numpy(g["t"]).cuda())              # taped forward (gradients: tests/test_train_gpu.py)
         assert out.requires_grad and out.shape == ref.shape
         assert float((out.detach().cpu() - ref).norm() / ref.norm()) <= 3e-2
+
+
+def test_scale_shift_norm_under_the_graph_sampler(monkeypatch):
+    """The fused CUDA-graph sampler with a use_scale_shift_norm=True model equals the eager launch sequence (the
+    per-sample affine parameters are built by small tensor ops inside the captured region)."""
+    from guided_diffusion.script_util import create_gaussian_diffusion
+    from guided_diffusion.wunet import WavUNetModel
+    cfg = dict(SMALL_CFG, use_scale_shift_norm=True)
+    m = WavUNetModel(**cfg)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(ow.tie_output_blocks(ow.seeded_state_dict(shapes, seed=0), len(cfg["channel_mult"])))
+    m.to("cuda").eval()
+    g = torch.Generator().manual_seed(1)
+    noise = torch.randn(2, 8, 8, 8, 8, generator=g).cuda()
+    cond = torch.rand(2, 24, 8, 8, 8, generator=g).cuda()
+    outs = []
+    for no_graph in ("0", "1"):
+        monkeypatch.setenv("FCWDM_NO_GRAPH", no_graph)
+        d = create_gaussian_diffusion(steps=10, predict_xstart=True, sample_schedule="sampled", mode="i2i")
+        torch.manual_seed(3)
+        outs.append(d.p_sample_loop(m, (2, 8, 8, 8, 8), noise=noise, cond=cond, progress=False))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(outs[0]).all())
+    assert float((outs[0] - outs[1]).abs().max()) <= 5e-2
