@@ -33,6 +33,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "fast-cwdm_b200")]
 
+if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:][:1] == ["reference"]:
+    # the reference moves its Haar band matrices to the GPU whenever one is visible, even for CPU inputs
+    # (DWT_IDWT/DWT_IDWT_layer.py:505-511): the CPU arm must not see a device
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -62,8 +67,10 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc, self.t_mark = index, [], None, 0.0
+    def __init__(self, index, enabled=True):
+        """enabled=False on ranks > 0: the JSON line reports rank 0's GPU, and N concurrent nvidia-smi loops slow each
+        other down enough to miss a short timed region."""
+        self.index, self.rows, self.proc, self.t_mark, self.enabled = index, [], None, 0.0, enabled
 
     def mark(self):
         """The timed region starts now: only samples arriving from here on are reported.  (The sampler is started
@@ -71,6 +78,8 @@ class ClockSampler:
         self.t_mark = time.time()
 
     def start(self):
+        if not self.enabled:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -85,9 +94,17 @@ class ClockSampler:
 
     def stop(self):
         if self.proc is not None:
-            time.sleep(0.12)                       # let the sample covering the end of the region arrive
+            # let the sample covering the end of the region arrive; on a busy 8-GPU box nvidia-smi's loop can take a few
+            # hundred ms per line, so wait (bounded) until at least one line has arrived after mark()
+            deadline = time.time() + 1.5
+            time.sleep(0.12)
+            while time.time() < deadline and not any(t >= self.t_mark for t, _ in self.rows):
+                time.sleep(0.05)
             self.proc.terminate()
         rows = [r for t, r in self.rows if t >= self.t_mark]
+        during = True
+        if not rows and self.rows:              # region shorter than the sampling period: fall back to the warm-up samples
+            rows, during = [r for _, r in self.rows[-3:]], False
         sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         reasons = []
@@ -95,7 +112,7 @@ class ClockSampler:
             if any(len(r) > col and r[col].lower().startswith("active") for r in rows):
                 reasons.append(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "during_timed_region": during}
 
 
 def ncu_traffic(name):
@@ -155,63 +172,116 @@ def oracle_state():
     return ow.tie_output_blocks(ow.seeded_state_dict(shapes, seed=0, std=0.02), 4)
 
 
-def cpu_step_seconds(sd, depth):
-    """One reference denoising step (U-Net forward + IDWT/clamp/DWT/posterior/noise) on a depth slab of the latent
-    volume, torch CPU, all host threads.  Returns seconds."""
-    from oracle import diffusion as od
-    from oracle import wunet as ow
-    tab = od.Tables(od.named_beta_schedule("linear", T_STEPS, "sampled"))
-    g = torch.Generator().manual_seed(1)
-    x = torch.randn((1, 8, depth) + LATENT[1:], generator=g)
-    cond = torch.rand((1, 24, depth) + LATENT[1:], generator=g)
-    model = lambda xin, tt: ow.wunet_forward(sd, xin, tt, model_channels=64, channel_mult=(1, 2, 2, 4))
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        od.p_sample(tab, model, x, torch.tensor([T_STEPS - 1]), cond=cond)
-    return time.perf_counter() - t0
+class ReferenceStep:
+    """One denoising step of config 2 (GaussianDiffusion.p_sample: WavUNetModel forward + IDWT / clamp / DWT + posterior
+    + noise, gaussian_diffusion.py:529-574) on the host CPU.  kind='reference': the UNMODIFIED reference's own classes
+    (oracle/_ref staged at build time, or the mount of the build container) through oracle/ref_shims; kind='port': the
+    oracle restatement, only when no copy of the reference is present."""
+
+    def __init__(self):
+        from oracle import ref_shims
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.sd = oracle_state()
+        self.kind = "reference" if ref_shims.reference_available() else "port"
+        self.ctx = None
+        if self.kind == "reference":
+            import contextlib
+            import io
+            self.ctx = ref_shims.reference_modules()
+            ref = self.ctx.__enter__()
+            args = ref.script_util.model_and_diffusion_defaults()
+            args.update(CFG_W4)
+            with contextlib.redirect_stdout(io.StringIO()):          # the reference prints its schedule diagnostics
+                self.model, self.diffusion = ref.script_util.create_model_and_diffusion(**args)
+            self.model.load_state_dict(self.sd, strict=True)
+            self.model.eval()
+            self.root = ref_shims.REFERENCE_ROOT
+
+    def close(self):
+        if self.ctx is not None:
+            self.ctx.__exit__(None, None, None)
+            self.ctx = None
+
+    def seconds(self, depth):
+        """Wall time of one step on a `depth`-plane slab of the 112-plane latent (depth % 16 == 0)."""
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn((1, 8, depth) + LATENT[1:], generator=g)
+        cond = torch.rand((1, 24, depth) + LATENT[1:], generator=g)
+        t = torch.tensor([T_STEPS - 1])
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            if self.kind == "reference":
+                out = self.diffusion.p_sample(self.model, x, t, clip_denoised=True, model_kwargs={}, cond=cond)
+            else:
+                from oracle import diffusion as od
+                from oracle import wunet as ow
+                tab = od.Tables(od.named_beta_schedule("linear", T_STEPS, "sampled"))
+                net = lambda xin, tt: ow.wunet_forward(self.sd, xin, tt, model_channels=64, channel_mult=(1, 2, 2, 4))
+                out = od.p_sample(tab, net, x, t, cond=cond)
+        dt = time.perf_counter() - t0
+        assert bool(torch.isfinite(out["sample"]).all())
+        return dt
 
 
 def cpu_baseline(budget_s=25.0):
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = oracle_state()
-    depth = 16                                           # 1/7 of the latent depth; must be divisible by 2^4
-    dt = cpu_step_seconds(sd, depth)
-    if dt * (LATENT[0] / depth) <= budget_s:             # fast host: time the full-depth step as well
-        depth = LATENT[0]
-        dt = cpu_step_seconds(sd, depth)
+    """cpu_baseline of the GPU arm's line: a bounded sample (one denoising step; a 16-plane slab first, the full 112
+    planes when that fits the budget) of the reference on the host cores, scaled to volumes/s."""
+    ref = ReferenceStep()
+    try:
+        depth = 16                                           # 1/7 of the latent depth; must be divisible by 2^4
+        dt = ref.seconds(depth)
+        if dt * (LATENT[0] / depth) <= budget_s:             # fast host: time the full-depth step as well
+            depth = LATENT[0]
+            dt = ref.seconds(depth)
+    finally:
+        ref.close()
     step_full = dt * (LATENT[0] / depth)
-    return {"value": 1.0 / (T_STEPS * step_full), "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"one reference denoising step (WavUNet fwd + IDWT/clamp/DWT + posterior) on a {depth}-plane "
-                      f"slab of the 112-plane latent, {dt:.2f} s, scaled x{LATENT[0] // depth} x T={T_STEPS}; "
-                      f"host {os.cpu_count()} logical cores"}
+    return {"value": 1.0 / (T_STEPS * step_full), "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": ref.kind,
+            "sample": f"one denoising step of the {'unmodified reference (GaussianDiffusion.p_sample, fp32 torch CPU)' if ref.kind == 'reference' else 'oracle port'} "
+                      f"on a {depth}-plane slab of the 112-plane latent, {dt:.2f} s, extrapolated x{LATENT[0] // depth} "
+                      f"x T={T_STEPS} identical steps to one volume; host {os.cpu_count()} logical cores"}
 
 
 def run_reference(args):
+    """The reference arm: rank 0 alone times the reference's own CPU implementation (other ranks exit without work).
+    One "step" of this arm = ONE denoising step (1/T of a volume): `ms_per_step` is that measured unit, and `value`
+    (volumes/s) = 1 / (T x step time) is an extrapolation over the T identical steps of a volume -- stated in config."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = oracle_state()
-    total = args.steps + args.warmup
-    depth = 16
-    probe = cpu_step_seconds(sd, depth)                  # also serves as the page-in warm-up
-    if probe * (LATENT[0] / depth) * total <= 240.0:
-        depth = LATENT[0]
-    for _ in range(args.warmup):
-        cpu_step_seconds(sd, depth)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_step_seconds(sd, depth)
-    per_step = (time.perf_counter() - t0) / max(1, args.steps)
-    vol_s = 1.0 / (T_STEPS * per_step * (LATENT[0] / depth))
-    sample = (f"each step = one reference denoising step on a {depth}-plane slab of the 112-plane latent "
-              f"({per_step:.2f} s), scaled x{LATENT[0] // depth} x T={T_STEPS} to volumes/s")
+    ref = ReferenceStep()
+    try:
+        total = args.steps + args.warmup
+        depth = 16
+        probe = ref.seconds(depth)                           # also serves as the page-in warm-up
+        if probe * (LATENT[0] / depth) * total <= 240.0:
+            depth = LATENT[0]
+        for _ in range(args.warmup):
+            ref.seconds(depth)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ref.seconds(depth)
+        per_step = (time.perf_counter() - t0) / max(1, args.steps)
+    finally:
+        ref.close()
+    scale = LATENT[0] / depth
+    vol_s = 1.0 / (T_STEPS * per_step * scale)
+    what = ("unmodified reference (GaussianDiffusion.p_sample + WavUNetModel, fp32 torch CPU)" if ref.kind == "reference"
+            else "oracle port (no copy of the reference present)")
+    sample = (f"each timed step = one denoising step of the {what} on a {depth}-plane slab of the 112-plane latent "
+              f"({per_step:.2f} s); volumes/s = 1 / (T={T_STEPS} x {scale:.0f} x step time), an extrapolation over identical steps")
+    n_gpus = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     print(json.dumps({"impl": "reference", "metric": "sampled 224x224x160 volumes/sec", "value": vol_s,
-                      "unit": "volumes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                      "ms_per_step": 1e3 / vol_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                      "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "arm": "oracle port on CPU"},
+                      "unit": "volumes/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": WORKLOAD, "arm": what,
+                                 "step_unit": f"one denoising step = 1/{T_STEPS} of a volume"
+                                              + ("" if depth == LATENT[0] else f", on {depth}/{LATENT[0]} of the depth"),
+                                 "host_arm_note": ("ONE host runs this arm whatever N is: at N > 1 a GPU/CPU ratio divides N "
+                                                   "GPUs by one host's cores and says nothing about scaling")},
                       "cpu_baseline": {"value": vol_s, "unit": "volumes/s", "cores": torch.get_num_threads(),
-                                       "kind": "port", "sample": sample},
+                                       "kind": ref.kind, "sample": sample},
                       "e2e": {"value": vol_s, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -219,30 +289,44 @@ def run_reference(args):
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
 def time_dominant_kernel(device, iters=20):
-    """conv3d 64->64 3x3x3 @112x112x80 alone: CUDA events on the launching stream, inputs (128 MB) ~ L2 size and
-    a 256 MB L2 flush between launches."""
+    """conv3d 64->64 3x3x3 @112x112x80 alone, in the two forms the denoising step actually launches (5 + 5 of its 10
+    full-resolution launches; `conv3d_pair_kernel<64, GN_IN>`): (A) a ResBlock's first conv = fused input GroupNorm+SiLU
+    + bias + per-sample timestep embedding + output statistics; (B) its second conv = fused input GroupNorm+SiLU + bias
+    + residual + output statistics.  CUDA events on the launching stream; a 256 MB write flushes L2 before every timed
+    launch.  Returns ({variant: ms}, flop per launch)."""
     from fcwdm import ops
     S = LATENT[0] * LATENT[1] * LATENT[2]
+    G = 32
     x = torch.randn((S, 64), device=device).to(torch.bfloat16)
+    res = torch.randn((S, 64), device=device).to(torch.bfloat16)
     w = torch.randn((64, 64, 3, 3, 3), device=device) * 0.02
     wp = ops.conv3d_pair_pack_weights(w)
-    b = torch.zeros(64, device=device)
+    b = torch.randn(64, device=device) * 0.1
+    emb = torch.randn((1, 64), device=device) * 0.1
+    gamma, beta = torch.rand(64, device=device) + 0.5, torch.randn(64, device=device) * 0.1
+    stats = torch.empty((1, ops.GN_STAT_REPLICAS, G, 2), dtype=torch.float64, device=device)
+    ops.groupnorm_stats(x, stats, 1, S, 64, G)
+    ostats = torch.zeros((1, ops.GN_STAT_REPLICAS, G, 2), dtype=torch.float64, device=device)
     y = torch.empty((S, 64), dtype=torch.bfloat16, device=device)
     flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=device)
-    for _ in range(3):
-        ops.conv3d_pair_cl(x, wp, b, y, (1,) + LATENT, 64, 64)
-    total = 0.0
-    for _ in range(iters):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ops.conv3d_pair_cl(x, wp, b, y, (1,) + LATENT, 64, 64)
-        e1.record()
-        e1.synchronize()
-        total += e0.elapsed_time(e1)
-    ms = total / iters
-    flop = 2.0 * S * 64 * 64 * 27
-    return ms, flop
+    gn_in = (stats, gamma, beta, G, 1e-5)
+    variants = {"gn_in+emb+stats": dict(gn_in=gn_in, chan_bias=emb, gn_stats=ostats, gn_groups=G),
+                "gn_in+residual+stats": dict(gn_in=gn_in, residual=res, gn_stats=ostats, gn_groups=G)}
+    out = {}
+    for name, kw in variants.items():
+        for _ in range(3):
+            ops.conv3d_pair_cl(x, wp, b, y, (1,) + LATENT, 64, 64, **kw)
+        total = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.conv3d_pair_cl(x, wp, b, y, (1,) + LATENT, 64, 64, **kw)
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        out[name] = total / iters
+    return out, 2.0 * S * 64 * 64 * 27
 
 
 def time_haar(device, iters=10):
@@ -336,7 +420,7 @@ def run_gpu(args):
         return float(ms)
 
     torch.manual_seed(1234 + rank)
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local, enabled=(rank == 0))
     warm = max(args.warmup, 3)
     clocks.start()
     timed(volume_resident, 0, warm)                      # lazy init, weight packing, CUDA-graph capture
@@ -375,21 +459,41 @@ def run_gpu(args):
         }
     if world > 1:
         dist.barrier()
+    # ---- config 3 (8 volumes per GPU) and config 4 (training step, data-parallel over the same N ranks), every rank
+    sec_batch8 = sec_train = None
+    if MODEL["name"] == "wunet" and args.batch == 1 and not args.no_secondary:
+        sec_batch8 = measure_batch8(model, diffusion, device, world, rank, barrier)
+        for smp in list(diffusion._samplers.values()):       # drop the captured graphs and their private pools
+            smp.release()
+        diffusion._samplers.clear()
+        stream._slots = None
+        torch.cuda.empty_cache()
+        sec_train = measure_train(device, world, rank, local, steps=10, warm=3, batch=2)
     if rank == 0:
-        ms_k, flop = time_dominant_kernel(device)
+        ms_v, flop = time_dominant_kernel(device)
+        ms_k = sum(ms_v.values()) / len(ms_v)                 # the step launches the two variants 5 : 5
         ach = flop / (ms_k * 1e-3) / 1e12
         result["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                              "frac": ach / peaks["tf_burst"], "traffic": ncu_traffic("r01_conv_pair64_ncu.txt"),
-                              "traffic_note": "dram__bytes_read+write of one launch, ncu --set full (profiles/"
-                                              "r01_conv_pair64_ncu.txt); algorithmic 257 MB",
-                              "kernel": "conv3d_pair_kernel<64> (cta_group::2, kd-fused) 64->64 @112x112x80",
-                              "us_per_launch": ms_k * 1e3, "flop_per_launch": flop}
+                              "frac": ach / peaks["tf_burst"], "traffic": ncu_traffic("r02_conv_pair64_gnin_ncu.txt"),
+                              "traffic_note": "dram__bytes_read+write of one launch of the residual variant, ncu --set full "
+                                              "behind a 256 MB L2 flush (profiles/r02_conv_pair64_gnin_ncu.txt); "
+                                              "algorithmic 257 MB (385 MB with the residual operand)",
+                              "kernel": "conv3d_pair_kernel<64, GN_IN> (cta_group::2, kd-fused) 64->64 @112x112x80, the two "
+                                        "in-step forms weighted 5:5 (fused input GroupNorm+SiLU, bias, timestep embedding "
+                                        "or residual, output statistics)",
+                              "us_per_launch": ms_k * 1e3, "us_by_variant": {k: v * 1e3 for k, v in ms_v.items()},
+                              "flop_per_launch": flop, "l2": "256 MB flush before every timed launch",
+                              "peak_kind": "burst (kernel timed alone)",
+                              # the whole denoising step against the sustained peak: the number that bounds volumes/s
+                              "step_tflops": result["step_tflops"], "step_peak": peaks["tf_sustained"],
+                              "step_frac": result["step_tflops"] / peaks["tf_sustained"]}
         hb = time_haar(device)
         result["secondary"] = {"dwt3d_gbs": hb["dwt3d"], "idwt3d_gbs": hb["idwt3d"], "hbm_peak_gbs": peaks["hbm"],
                                "dwt3d_frac": hb["dwt3d"] / peaks["hbm"], "idwt3d_frac": hb["idwt3d"] / peaks["hbm"],
-                               "workload": "16 x 224x224x160 fp32 planar, 2*numel*4 bytes per launch"}
+                               "workload": "16 x 224x224x160 fp32 planar, 2*numel*4 bytes per launch",
+                               "batch8": sec_batch8, "train": sec_train}
         if world == 1 and not args.no_cpu_baseline and MODEL["name"] == "wunet":
-            result["cpu_baseline"] = cpu_baseline()
+            result["cpu_baseline"] = cpu_baseline_subprocess()
         else:
             result["cpu_baseline"] = None
         print(json.dumps(result))
@@ -424,19 +528,14 @@ def time_wgrad_kernel(device, iters=10):
     return total / iters, 2.0 * S * 64 * 64 * 27
 
 
-def run_train(args):
+def train_measure(device, world, rank, local, steps, warm, batch, want_roofline=False):
+    """Config 4 on this rank's GPU: `warm` + `steps` training steps (training_losses forward + fcwdm backward + fused AdamW
+    on `batch` synthetic cases; under world > 1 one bucketed NCCL gradient all-reduce per step), resident and end to end
+    (pinned-host batch uploaded and the loss read back every step).  Needs the default process group when world > 1.
+    Returns the result dict on rank 0, None elsewhere."""
     import torch.distributed as dist
     from fcwdm import ddp, native
     from fcwdm.optim import FusedAdamW
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the fcwdm training path has no CPU fallback")
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
     peaks = measured_peaks()
     model, diffusion = build_model(device)
     model.train()
@@ -446,7 +545,7 @@ def run_train(args):
         ddp.broadcast_parameters(model)
         sync = ddp.attach(model)
     opt = FusedAdamW(model, lr=1e-5, weight_decay=0.0)                      # run.sh:60 lr, train_util.py:75-82
-    B = args.batch
+    B = batch
     g = torch.Generator().manual_seed(100 + rank)                            # per-rank data (seed + rank)
     host = {k: torch.rand((B, 1) + IMAGE, generator=g).pin_memory() for k in ("t1n", "t1c", "t2w", "t2f")}
     dev_batch = {k: v.to(device) for k, v in host.items()}
@@ -527,48 +626,125 @@ def run_train(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    warm = max(args.warmup, 3)
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local, enabled=(rank == 0))
     clocks.start()
     timed(step_resident, 0, warm)
     clocks.mark()
     n0 = native.launch_count
-    ms_res = timed(step_resident, args.steps, 0)
+    ms_res = timed(step_resident, steps, 0)
     launches = native.launch_count - n0
-    clk = clocks.stop()
     for ev in slot_free:
         ev.record(torch.cuda.current_stream(device))
-    ms_e2e = timed(step_e2e, args.steps, 1)
+    ms_e2e = timed(step_e2e, steps, 1)
+    clk = clocks.stop()                           # covers the resident and the end-to-end timed regions
     loss_done[(pipe["i"] - 1) % 2].synchronize()
     last["host_loss"] = float(loss_cell[(pipe["i"] - 1) % 2])
     finite = bool(torch.isfinite(last["loss"])) and last["host_loss"] == float(last["loss"])
-    if rank == 0:
-        samples = args.steps * world * B
-        h2d = sum(v.numel() * 4 for v in host.values())
-        model_name = "UNetModel" if MODEL["name"] == "unet" else "WavUNetModel"
-        flop_step = 3.0 * (UNET_FLOP_PER_STEP if MODEL["name"] == "unet" else CONV_FLOP_PER_STEP) * B   # fwd + dgrad + wgrad
-        result = {
-            "metric": f"{model_name} training samples/sec", "value": samples / (ms_res * 1e-3), "unit": "samples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_res / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"training step (training_losses i2i + backward + AdamW), {model_name} "
-                                   f"{'(run.sh: 1,2,2,4,4)' if MODEL['name'] == 'unet' else 'CFG-W4'}, "
-                                   f"batch {B} x 224x224x160 per GPU, bf16 compute / fp32 master",
-                       "parallelism": f"dp{world}: one bucketed NCCL gradient all-reduce (mean) per step" if world > 1
-                       else "single GPU", "l2": "per-step activations ~6 GB >> 126 MB L2 (no flush needed)",
-                       "allreduce_buckets": sync.launched if sync else 0, "peaks": peaks["src"], "loss_finite": finite,
-                       "final_loss": float(last["loss"])},
-            "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches), "clocks": clk,
-            "step_tflops": flop_step * args.steps * world / (ms_res * 1e-3) / 1e12,
-        }
+    if rank != 0:
+        return None
+    samples = steps * world * B
+    h2d = sum(v.numel() * 4 for v in host.values())
+    model_name = "UNetModel" if MODEL["name"] == "unet" else "WavUNetModel"
+    flop_step = 3.0 * (UNET_FLOP_PER_STEP if MODEL["name"] == "unet" else CONV_FLOP_PER_STEP) * B   # fwd + dgrad + wgrad
+    result = {
+        "metric": f"{model_name} training samples/sec", "value": samples / (ms_res * 1e-3), "unit": "samples/s",
+        "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_res / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"training step (training_losses i2i + backward + AdamW), {model_name} "
+                               f"{'(run.sh: 1,2,2,4,4)' if MODEL['name'] == 'unet' else 'CFG-W4'}, "
+                               f"batch {B} x 224x224x160 per GPU, bf16 compute / fp32 master",
+                   "parallelism": f"dp{world}: one bucketed NCCL gradient all-reduce (mean) per step" if world > 1
+                   else "single GPU", "l2": "per-step activations ~6 GB >> 126 MB L2 (no flush needed)",
+                   "allreduce_buckets": sync.launched if sync else 0, "peaks": peaks["src"], "loss_finite": finite,
+                   "final_loss": float(last["loss"])},
+        "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "clocks": clk,
+        "step_tflops": flop_step * steps * world / (ms_res * 1e-3) / 1e12,
+    }
+    result["step_frac"] = result["step_tflops"] / world / peaks["tf_sustained"]
+    if want_roofline:
         ms_k, flop = time_wgrad_kernel(device)
         ach = flop / (ms_k * 1e-3) / 1e12
         result["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                               "frac": ach / peaks["tf_burst"], "traffic": None,
                               "kernel": "conv3d_wgrad64_kernel (tap-packed M=128/64 x N=192) + finalize, 64->64 @112x112x80",
                               "us_per_launch": ms_k * 1e3, "flop_per_launch": flop}
+    return result
+
+
+def measure_train(device, world, rank, local, steps, warm, batch):
+    """`secondary.train` of the default line (BASELINE config 4 at the same N): a short run of train_measure."""
+    r = train_measure(device, world, rank, local, steps, warm, batch)
+    if r is None:
+        return None
+    keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "e2e", "clocks", "gpu_launches",
+            "step_tflops", "step_frac")
+    out = {k: r[k] for k in keep}
+    out["config"] = r["config"]
+    return out
+
+
+def measure_batch8(model, diffusion, device, world, rank, barrier, steps=2, warm=2, batch=8):
+    """`secondary.batch8` (BASELINE config 3): `batch` volumes per GPU per p_sample_loop, inputs resident, every rank."""
+    import torch.distributed as dist
+    from fcwdm import pipeline
+    vol, noise = synth_volume(2000 + rank, batch)
+    vol, noise = vol.to(device), noise.to(device)
+
+    def run():
+        return pipeline.synthesize(diffusion, model, vol[:, 1:2], vol[:, 2:3], vol[:, 3:4], noise)
+
+    for _ in range(warm):
+        run()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = run()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    finite = bool(torch.isfinite(out).all())
+    for smp in [s for s in diffusion._samplers.values() if s.N == batch]:
+        smp.release()                                        # the batch-8 graph's private pool is not needed any more
+    return {"value": steps * world * batch / (ms * 1e-3), "unit": "volumes/s", "n_gpus": world, "steps": steps,
+            "warmup": warm, "volumes_per_step": batch, "ms_per_step": ms / steps, "output_finite": finite,
+            "workload": f"p_sample_loop T={T_STEPS}, {batch} volumes per GPU per call, inputs resident"}
+
+
+def cpu_baseline_subprocess():
+    """cpu_baseline of the default line: `bench.py --impl reference --steps 1 --warmup 0` in a child process with CUDA
+    hidden (the reference moves its band matrices to any visible GPU), i.e. ONE denoising step of the unmodified
+    reference on the host cores after a 16-plane probe (about 10-20 s), scaled to volumes/s."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                           capture_output=True, text=True, timeout=600, env=env)
+        line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1]
+        return json.loads(line)["cpu_baseline"]
+    except Exception as exc:
+        return {"value": None, "unit": "volumes/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": f"failed: {exc}"}
+
+
+def run_train(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the fcwdm training path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    result = train_measure(device, world, rank, local, args.steps, max(args.warmup, 3), args.batch, want_roofline=True)
+    if rank == 0:
         result["cpu_baseline"] = None
         print(json.dumps(result))
     if world > 1:
@@ -583,6 +759,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fcwdm", choices=["fcwdm", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip secondary.batch8 / secondary.train (configs 3, 4)")
     ap.add_argument("--batch", type=int, default=1, help="volumes per GPU per step (BASELINE config 3 uses 8)")
     ap.add_argument("--model", default="wunet", choices=["wunet", "unet"],
                     help="wunet = WavUNetModel CFG-W4 (the headline); unet = the plain UNetModel of run.sh (1,2,2,4,4)")

@@ -37,8 +37,8 @@ __device__ __forceinline__ void step_voxel(float* mo, const float* xt, const flo
 // One thread = 4 consecutive latent voxels along w (float4 per band plane).  Requires S % 4 == 0.
 template <bool kModelOutCl>
 __global__ void __launch_bounds__(256) p_sample_step_kernel(const void* __restrict__ model_out, int64_t mo_ld,
-                                                            const float* __restrict__ x_t,
-                                                            const float* __restrict__ noise, float* __restrict__ x_prev,
+                                                            const float* x_t,      // may alias x_prev (in-place update)
+                                                            const float* __restrict__ noise, float* x_prev,
                                                             float* __restrict__ pred_xstart,
                                                             __nv_bfloat16* __restrict__ x_prev_cl, int64_t xp_ld,
                                                             const float* __restrict__ coef,
@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(256) p_sample_step_kernel(const void* __restri
 // scalar tail-safe variant for S % 4 != 0 or unaligned pointers (one thread per voxel)
 template <bool kModelOutCl>
 __global__ void __launch_bounds__(256) p_sample_step_scalar(const void* __restrict__ model_out, int64_t mo_ld,
-                                                            const float* __restrict__ x_t,
-                                                            const float* __restrict__ noise, float* __restrict__ x_prev,
+                                                            const float* x_t,
+                                                            const float* __restrict__ noise, float* x_prev,
                                                             float* __restrict__ pred_xstart,
                                                             __nv_bfloat16* __restrict__ x_prev_cl, int64_t xp_ld,
                                                             const float* __restrict__ coef,

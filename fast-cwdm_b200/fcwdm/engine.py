@@ -43,6 +43,14 @@ class WavUNetEngine:
         self._stats = {}
         self._arena = None
         self._arena_pos = 0
+        self._emb_w = self._emb_b = None
+        self._ptrs = None
+        # generation: bumped whenever the packed operand copies are refreshed (parameters changed in place, by version or
+        # through invalidate()); buffers_id: bumped only when the persistent device buffers themselves are re-allocated.
+        # A captured CUDA graph (fcwdm.sampler) stays valid across generations -- the re-pack writes into the same
+        # buffers -- and must be re-captured only when buffers_id changes.
+        self.generation = 0
+        self.buffers_id = 0
         import os
         # fused GroupNorm statistics in the conv epilogue: measured break-even against the separate (HBM-roofline)
         # statistics pass in round 1, so opt-in
@@ -55,7 +63,7 @@ class WavUNetEngine:
 
     # ------------------------------------------------------------------ weights
     def _signature(self):
-        return tuple((id(p), p._version, p.device) for p in self.model.parameters())
+        return tuple((id(p), p._version, p.data_ptr()) for p in self.model.parameters())
 
     want_dgrad = False      # the training engine also keeps the data-gradient form of every conv weight
 
@@ -64,6 +72,10 @@ class WavUNetEngine:
         if sig == self._sig and self._device == device:
             return
         self._f32.clear()
+        ptrs = tuple(s[2] for s in sig)
+        if ptrs != self._ptrs:            # parameter storage moved (.to(), FusedAdamW re-laying): bias / GroupNorm aliases are new
+            self._ptrs = ptrs
+            self.buffers_id += 1
         convs = [m for m in self.model.modules() if isinstance(m, torch.nn.Conv3d)]
         layout = (str(device), self.want_dgrad, self.use_pair) + tuple(
             (id(m), m.weight.data_ptr(), tuple(m.weight.shape), m.weight.dtype) for m in convs)
@@ -99,6 +111,8 @@ class WavUNetEngine:
             self._jobs = torch.tensor(jobs, dtype=torch.int64).to(device)
             self._jobs_max = max(j[7] for j in jobs)
             self._layout = layout
+            self._emb_w = self._emb_b = None
+            self.buffers_id += 1
         with ops._on(device) as st:
             native.call("fcwdm_conv3d_pack_all", ops._ptr(self._jobs), self._jobs.shape[0], self._jobs_max, st)
         for mod in convs:
@@ -118,14 +132,22 @@ class WavUNetEngine:
                     pad = off - self._emb_off[id(mod)][0] - lin.out_features
                     ws.append(torch.zeros((pad, lin.in_features), device=device))
                     bs.append(torch.zeros((pad,), device=device))
-        self._emb_w = torch.cat(ws, dim=0).contiguous()
-        self._emb_b = torch.cat(bs, dim=0).contiguous()
+        # persistent buffers, refreshed in place: a captured graph holds their addresses
+        emb_w, emb_b = torch.cat(ws, dim=0), torch.cat(bs, dim=0)
+        if self._emb_w is None or self._emb_w.shape != emb_w.shape or self._emb_w.device != emb_w.device:
+            self._emb_w, self._emb_b = emb_w.contiguous(), emb_b.contiguous()
+            self.buffers_id += 1
+        else:
+            self._emb_w.copy_(emb_w)
+            self._emb_b.copy_(emb_b)
         self._sig = sig
         self._device = device
+        self.generation += 1
 
     def invalidate(self):
         """The parameters were updated through raw pointers (e.g. fcwdm.optim.FusedAdamW): re-pack on the next call."""
         self._sig = None
+        self.generation += 1
 
     def _p32(self, p):
         """fp32 contiguous view of a (GroupNorm / Linear) parameter."""

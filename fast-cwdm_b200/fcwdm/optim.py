@@ -62,9 +62,56 @@ class FusedAdamW:
                 eng.invalidate()
 
     def state_dict(self):
-        return {"step": self.step_count, "m": self.m, "v": self.v, "lr": self.param_groups[0]["lr"]}
+        """The layout ``torch.optim.AdamW(model.parameters()).state_dict()`` has (what the reference's TrainLoop writes to
+        ``opt_best_<contr>.pt`` / ``optNNNNNN.pt``, train_util.py:75-82,507-523): per-parameter ``step`` / ``exp_avg`` /
+        ``exp_avg_sq`` under integer ids in ``model.parameters()`` order, one param group.  The tensors are views of the
+        flat moment buffers (torch.save serialises them individually)."""
+        params = list(self.model.parameters())
+        state = {}
+        if self.step_count > 0:
+            for i, (p, (lo, hi)) in enumerate(zip(params, self.offsets)):
+                state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.m[lo:hi].view(p.shape),
+                            "exp_avg_sq": self.v[lo:hi].view(p.shape)}
+        group = {"lr": self.param_groups[0]["lr"], "betas": tuple(self.betas), "eps": self.eps,
+                 "weight_decay": self.weight_decay, "amsgrad": False, "maximize": False, "foreach": None,
+                 "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": True,
+                 "params": list(range(len(params)))}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
+        """Accepts a ``torch.optim.AdamW`` state dict (written by the reference or by ``state_dict`` above) or the flat
+        ``{step, m, v, lr}`` form earlier builds of this package wrote.  Sizes are validated before anything is copied."""
+        params = list(self.model.parameters())
+        if "state" in sd and "param_groups" in sd:
+            ids = [i for g in sd["param_groups"] for i in g["params"]]
+            if len(ids) != len(params):
+                raise ValueError(f"optimizer state has {len(ids)} parameters, the model has {len(params)}")
+            for pos, pid in enumerate(ids):
+                st = sd["state"].get(pid)
+                if st is not None and tuple(st["exp_avg"].shape) != tuple(params[pos].shape):
+                    raise ValueError(f"optimizer state of parameter {pos}: shape {tuple(st['exp_avg'].shape)} does not "
+                                     f"match the model's {tuple(params[pos].shape)}")
+            steps = set()
+            self.m.zero_()
+            self.v.zero_()
+            for pos, pid in enumerate(ids):
+                st = sd["state"].get(pid)
+                if st is None:
+                    continue
+                lo, hi = self.offsets[pos]
+                self.m[lo:hi].copy_(st["exp_avg"].reshape(-1))
+                self.v[lo:hi].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(st["step"])))
+            if len(steps) > 1:
+                raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): FusedAdamW keeps one step counter")
+            self.step_count = steps.pop() if steps else 0
+            self.param_groups[0]["lr"] = sd["param_groups"][0].get("lr", self.lr)
+            return
+        if not {"step", "m", "v"} <= set(sd):
+            raise ValueError("unrecognised optimizer state: expected a torch.optim.AdamW state_dict ('state', "
+                             "'param_groups') or the flat fcwdm form ('step', 'm', 'v')")
+        if sd["m"].numel() != self.m.numel() or sd["v"].numel() != self.v.numel():
+            raise ValueError(f"flat optimizer state has {sd['m'].numel()} elements, this model needs {self.m.numel()}")
         self.step_count = int(sd["step"])
         self.m.copy_(sd["m"])
         self.v.copy_(sd["v"])

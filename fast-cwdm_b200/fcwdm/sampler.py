@@ -23,15 +23,41 @@ from . import ops
 class FusedSampler:
     _cache_attr = "_samplers"
 
+    noise_hook = None       # optional callable(noise_buffer, diffusion_index) that fills the step's noise in place
+    MAX_CACHED = 2          # per diffusion object: each entry pins ~0.3 GB of state + a CUDA graph's private pool (GBs)
+
     @classmethod
     def get(cls, diffusion, model, shape, device, clip_denoised, i2i):
-        key = (id(model), tuple(shape), str(device), bool(clip_denoised), bool(i2i), model.engine()._signature())
+        """One sampler per (model object, shape, device, clip, i2i).  Weight updates (load_state_dict, optimizer steps)
+        do NOT create a new entry: the engine re-packs into its persistent buffers and the captured graph stays valid;
+        only when the engine's buffers were re-allocated is the graph dropped and re-captured (see ``_sync_weights``).
+        The cache is an LRU of MAX_CACHED entries; an evicted sampler's graph and buffers are released."""
+        key = (id(model), tuple(shape), str(device), bool(clip_denoised), bool(i2i))
         cache = getattr(diffusion, cls._cache_attr)
-        s = cache.get(key)
+        s = cache.pop(key, None)
+        if s is not None and s.model is not model:          # id() reuse after the old model was collected
+            s.release()
+            s = None
         if s is None:
             s = cls(diffusion, model, shape, device, clip_denoised, i2i)
-            cache[key] = s
+        cache[key] = s                                      # most recently used last
+        while len(cache) > cls.MAX_CACHED:
+            cache.pop(next(iter(cache))).release()
         return s
+
+    def release(self):
+        self.graph = None
+        self.x_in = self.x_t = self.pred = self.noise = None
+
+    def _sync_weights(self):
+        """Bring the engine's packed operand copies up to date OUTSIDE the graph (the captured launch sequence only reads
+        them) and drop the graph if the buffers it references were re-allocated."""
+        eng = self.engine
+        eng.prepare(self.device)
+        if eng.buffers_id != self._buffers_id:
+            self.graph = None
+            self._eager_steps = 0
+            self._buffers_id = eng.buffers_id
 
     def __init__(self, diffusion, model, shape, device, clip_denoised, i2i):
         from guided_diffusion.gaussian_diffusion import ModelMeanType
@@ -45,21 +71,31 @@ class FusedSampler:
         self.engine = model.engine()
         ld_in = (model.in_channels + 63) // 64 * 64
         self.x_in = torch.zeros((N * self.S, ld_in), dtype=torch.bfloat16, device=device)
+        # the step kernel is per-voxel local, so x_{t-1} overwrites x_t in place: no second state buffer, no copy
         self.x_t = torch.empty(shape, dtype=torch.float32, device=device)
-        self.x_next = torch.empty(shape, dtype=torch.float32, device=device)
-        self.pred = torch.empty(shape, dtype=torch.float32, device=device)
+        self.pred = None                                  # allocated on the first step that asks for pred_xstart
+        self.want_pred = True
         self.noise = torch.empty(shape, dtype=torch.float32, device=device)
         self.t_diff = torch.zeros((N,), dtype=torch.int64, device=device)
         self.t_model = torch.zeros((N,), dtype=torch.int64, device=device)
         self.coef = diffusion._table("step", device)
         self.graph = None
         self._eager_steps = 0
+        self._buffers_id = -1
         self.use_graph = os.environ.get("FCWDM_NO_GRAPH", "0") != "1"
         self.launches_per_step = None
 
     # ------------------------------------------------------------------
-    def begin(self, noise, cond):
-        """Load a new volume batch: x_T and (i2i) the 24 conditioning channels."""
+    def begin(self, noise, cond, want_pred=True):
+        """Load a new volume batch: x_T and (i2i) the 24 conditioning channels.  want_pred=False (p_sample_loop, which
+        only returns the final sample): the step kernel does not materialise pred_xstart (32 MB less per step)."""
+        self._sync_weights()
+        if bool(want_pred) != self.want_pred:
+            self.want_pred = bool(want_pred)
+            self.graph = None                             # the captured step kernel carries the pred pointer
+            self._eager_steps = min(self._eager_steps, 1)
+        if self.want_pred and self.pred is None:
+            self.pred = torch.empty(self.shape, dtype=torch.float32, device=self.device)
         self.x_t.copy_(noise)
         ops.planar_to_cl(self.x_t, self.x_in, 8)
         if self.i2i:
@@ -75,7 +111,8 @@ class FusedSampler:
         d, h, w = self.dims
         with ops._on(self.device) as st:
             native.call("fcwdm_p_sample_step", ops._ptr(out_cl), out_cl.stride(0), ops._ptr(self.x_t),
-                        ops._ptr(self.noise), ops._ptr(self.x_next), ops._ptr(self.pred), ops._ptr(self.x_in),
+                        ops._ptr(self.noise), ops._ptr(self.x_t), ops._ptr(self.pred if self.want_pred else None),
+                        ops._ptr(self.x_in),
                         self.x_in.stride(0), ops._ptr(self.coef), ops._ptr(self.t_diff), self.coef.shape[0], self.N, d, h,
                         w, 1 if self.clip else 0, 1 if self.predict_xstart else 0, st)
         self.launches_per_step = native.launch_count - n0
@@ -87,7 +124,10 @@ class FusedSampler:
         captured once (capture records, it does not execute) and every later step is a graph replay."""
         self.t_diff.fill_(int(i))
         self.t_model.fill_(int(t_model))
-        self.noise.normal_()                      # == th.randn_like(x): same generator, same draw order
+        if self.noise_hook is not None:
+            self.noise_hook(self.noise, int(i))   # tests / reproducibility: the caller supplies this step's noise
+        else:
+            self.noise.normal_()                  # == th.randn_like(x): same generator, same draw order
         if not self.use_graph or self._eager_steps == 0:
             self._step_body()
             self._eager_steps += 1
@@ -98,7 +138,6 @@ class FusedSampler:
                     self._step_body()
                 self.graph = g
             self.graph.replay()
-        self.x_t.copy_(self.x_next)               # graph buffers have fixed addresses: x_t is always the input
-        if clone:
-            return {"sample": self.x_next.clone(), "pred_xstart": self.pred.clone()}
-        return {"sample": self.x_next, "pred_xstart": self.pred}
+        if clone:                                 # the generator API hands out tensors the caller may keep
+            return {"sample": self.x_t.clone(), "pred_xstart": self.pred.clone() if self.want_pred else None}
+        return {"sample": self.x_t, "pred_xstart": self.pred if self.want_pred else None}

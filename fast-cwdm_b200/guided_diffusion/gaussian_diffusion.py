@@ -270,16 +270,21 @@ class GaussianDiffusion:
         scripts/complete_dataset.py:270-278 does.  Here ``time`` defaults to None = num_timesteps, which is
         identical for T = 1000 and fixes the IndexError for every other T."""
         final = None
-        for sample in self.p_sample_loop_progressive(model, shape, noise=noise, clip_denoised=clip_denoised,
-                                                     denoised_fn=denoised_fn, cond_fn=cond_fn,
-                                                     model_kwargs=model_kwargs, device=device, progress=progress,
-                                                     cond=cond):
+        for sample in self._sample_loop(model, shape, None, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs,
+                                        device, progress, cond, lean=True):
             final = sample
-        return final["sample"]
+        return final["sample"].clone() if final.get("_view") else final["sample"]
 
     def p_sample_loop_progressive(self, model, shape, time=None, noise=None, clip_denoised=True, denoised_fn=None,
                                   cond_fn=None, model_kwargs=None, device=None, progress=True, cond=None):
         """Generator over the per-step dicts of p_sample (reference :668-719)."""
+        return self._sample_loop(model, shape, time, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device,
+                                 progress, cond, lean=False)
+
+    def _sample_loop(self, model, shape, time, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device, progress,
+                     cond, lean):
+        """lean=True (p_sample_loop: only the last sample is used): the fused sampler yields views of its state buffer
+        instead of per-step clones and does not materialise pred_xstart."""
         if time is None:
             time = self.num_timesteps
         inner, tmap, rescale, _ = _unwrap(model)
@@ -308,9 +313,11 @@ class GaussianDiffusion:
             with th.no_grad():
                 sampler = FusedSampler.get(self, inner, tuple(img.shape), img.device, clip_denoised,
                                            self.mode == 'i2i')
-                sampler.begin(img, cond if self.mode == 'i2i' else None)
+                sampler.begin(img, cond if self.mode == 'i2i' else None, want_pred=not lean)
                 for i in indices:
-                    out = sampler.step(i, tmap[i] if tmap is not None else i)
+                    out = sampler.step(i, tmap[i] if tmap is not None else i, clone=not lean)
+                    if lean:
+                        out["_view"] = True
                     yield out
             return
         for i in indices:

@@ -68,7 +68,7 @@ def _default_channel_mult(image_size):
 def create_model(image_size, num_channels, num_res_blocks, channel_mult="", learn_sigma=False, class_cond=False,
                  use_checkpoint=False, attention_resolutions="16", num_heads=1, num_head_channels=-1,
                  num_heads_upsample=-1, use_scale_shift_norm=False, dropout=0, resblock_updown=True, use_fp16=False,
-                 use_new_attention_order=False, dims=2, num_groups=32, in_channels=1, out_channels=0,
+                 use_new_attention_order=False, num_groups=32, dims=2, in_channels=1, out_channels=0,
                  bottleneck_attention=True, resample_2d=True, additive_skips=False, use_freq=False):
     if not channel_mult:
         channel_mult = _default_channel_mult(image_size)

@@ -19,6 +19,7 @@ against this module unchanged; what is different, and why:
 """
 import functools
 import os
+import re
 import time
 
 import numpy as np
@@ -154,14 +155,36 @@ class TrainLoop:
     def _load_and_sync_parameters(self):
         resume_checkpoint = find_resume_checkpoint() or self.resume_checkpoint
         if resume_checkpoint:
-            self.resume_step = parse_resume_step_from_filename(resume_checkpoint) or self.resume_step
+            self.resume_step = resume_step_of_checkpoint(resume_checkpoint, self.resume_step)
             logger.log(f"loading model from checkpoint: {resume_checkpoint}...")
             self.model.load_state_dict(dist_util.load_state_dict(resume_checkpoint, map_location=self.device))
         dist_util.sync_params(self.model.parameters())
+        self._decorrelate_ranks()
         for name in ("_engine", "_train_engine"):        # packed weights follow the new values
             eng = getattr(self.model, name, None)
             if eng is not None:
                 eng.invalidate()
+
+    def _decorrelate_ranks(self):
+        """scripts/train.py seeds torch / numpy / random with the SAME ``args.seed`` in every process (train.py:26-29) and
+        builds a shuffling DataLoader without a DistributedSampler, so under torchrun every rank would draw the same
+        cases, timesteps and noise and the all-reduce would average identical gradients.  After the weight broadcast the
+        generators are therefore advanced by a rank-dependent offset (seed + rank); rank 0 keeps
+        the single-process stream, so a world of one is unchanged."""
+        world, rank = _world(), _rank()
+        if world <= 1:
+            return
+        if rank:
+            import random
+            th.manual_seed(th.initial_seed() + rank)
+            th.cuda.manual_seed(th.cuda.initial_seed() + rank)
+            np.random.seed((int(np.random.get_state()[1][0]) + rank) % (2 ** 32))
+            random.seed(random.getrandbits(32) + rank)
+        sampler = getattr(self.datal, "sampler", None)
+        from torch.utils.data.distributed import DistributedSampler
+        if sampler is not None and not isinstance(sampler, DistributedSampler) and rank == 0:
+            logger.warn("the data loader has no DistributedSampler: ranks draw independently shuffled cases (re-seeded "
+                        "per rank), so one epoch visits each case ~world_size times instead of once")
 
     def _load_optimizer_state(self):
         main_checkpoint = find_resume_checkpoint() or self.resume_checkpoint
@@ -375,6 +398,24 @@ def parse_resume_step_from_filename(filename):
             break
         digits = c + digits
     return int(digits) if digits else 0
+
+
+_STEP_FIELD = re.compile(r"_(\d{6})(?:_|\.|$)")
+
+
+def resume_step_of_checkpoint(filename, fallback=0):
+    """Global step a checkpoint was written at, for the names THIS class writes: ``<dataset>_<contr>_<NNNNNN>_<schedule>_
+    <T>.pt`` (``save``) carries it as its 6-digit field; ``..._BEST_<schedule>_<T>.pt`` (``save_if_best``) carries none,
+    so the caller's ``resume_step`` stands.  ``parse_resume_step_from_filename`` -- kept as the reference defines it --
+    would return the diffusion step count T for both (their last '_' word); it is only used for other names
+    (``model012000.pt``)."""
+    base = os.path.basename(filename)
+    m = _STEP_FIELD.search(base)
+    if m:
+        return int(m.group(1))
+    if "_BEST_" in base:
+        return fallback
+    return parse_resume_step_from_filename(filename) or fallback
 
 
 def get_blob_logdir():

@@ -101,6 +101,8 @@ int fcwdm_idwt3d_cl(const void* lll, int64_t lll_ld, const void* hi, int64_t hi_
  * x_t, noise, x_prev, pred_xstart (optional): planar f32 (N,8,d,h,w).
  * x_prev_cl (optional): bf16 channels-last copy of x_prev written to x_prev_cl[voxel*xp_cl_ld + band], the
  * first 8 channels of the persistent denoiser input (replaces th.cat([x, cond]), :297).
+ * x_prev may alias x_t (the update is local to one latent voxel, so the chain state is updated in place);
+ * pred_xstart may be NULL.
  * ---------------------------------------------------------------------------------------------------- */
 int fcwdm_p_sample_step(const void* model_out, int64_t mo_cl_ld, const float* x_t, const float* noise,
                         float* x_prev, float* pred_xstart, void* x_prev_cl, int64_t xp_cl_ld,

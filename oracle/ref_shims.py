@@ -7,9 +7,10 @@ taps are used, DWT_IDWT/DWT_IDWT_layer.py:451-453,553-557), ``blobfile`` (dist_u
 stub modules for those names, then puts the reference root first on ``sys.path`` so that
 ``import DWT_IDWT.DWT_IDWT_layer`` / ``import guided_diffusion.*`` resolve to the reference's own files.
 
-It is used by ``oracle/make_golden.py`` (fixture generation) and by CPU tests that cross-check the oracle
-restatement against the real reference when ``/root/reference`` exists.  It never runs on the GPU box
-(the reference does not travel) and nothing in the product path may import it.
+It is used by ``oracle/make_golden*.py`` (fixture generation), by CPU tests that cross-check the oracle
+restatement against the real reference, and by ``bench.py --impl reference`` (the CPU arm), which on the GPU box
+finds the byte-for-byte staged copy ``oracle/_ref/`` made by ``stage_reference()`` at build time.  Nothing in the
+product path may import it.
 """
 import contextlib
 import importlib
@@ -17,7 +18,50 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("FCWDM_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED_ROOT = os.path.join(_HERE, "_ref")          # git-ignored copy made by stage_reference() (travels to the GPU box)
+_PACKAGES = ("DWT_IDWT", "guided_diffusion")
+
+
+def _pick_root():
+    """$FCWDM_REFERENCE_ROOT, else the read-only mount of the build container, else the staged copy."""
+    env = os.environ.get("FCWDM_REFERENCE_ROOT")
+    if env:
+        return env
+    for root in ("/root/reference", STAGED_ROOT):
+        if os.path.isdir(os.path.join(root, "guided_diffusion")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
+
+
+def stage_reference(src="/root/reference"):
+    """Copy the two Python packages of the UNMODIFIED reference that the hot path lives in into oracle/_ref/ (git-ignored,
+    not gpurun-ignored), so that bench.py --impl reference can time the reference's own code on the GPU box's host
+    cores.  Called by __graft_entry__.build() in the build container; a no-op where the reference is not mounted.
+    Nothing is edited: files are byte-for-byte copies, verified by size + sha256 in _ref/MANIFEST.json."""
+    import hashlib
+    import json
+    import shutil
+    if not os.path.isdir(os.path.join(src, "guided_diffusion")):
+        return None
+    manifest = {}
+    for pkg in _PACKAGES:
+        dst_dir = os.path.join(STAGED_ROOT, pkg)
+        os.makedirs(dst_dir, exist_ok=True)
+        for name in sorted(os.listdir(os.path.join(src, pkg))):
+            if not name.endswith(".py"):
+                continue
+            s, d = os.path.join(src, pkg, name), os.path.join(dst_dir, name)
+            data = open(s, "rb").read()
+            if not os.path.exists(d) or open(d, "rb").read() != data:
+                shutil.copyfile(s, d)
+            manifest[f"{pkg}/{name}"] = {"bytes": len(data), "sha256": hashlib.sha256(data).hexdigest()}
+    with open(os.path.join(STAGED_ROOT, "MANIFEST.json"), "w") as fh:
+        json.dump({"source": src, "files": manifest}, fh, indent=1, sort_keys=True)
+    return STAGED_ROOT
 
 # pywavelets 1.4.1 (environment.yml:11) values for pywt.Wavelet('haar')
 _S = 0.7071067811865476

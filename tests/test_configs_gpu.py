@@ -1,0 +1,262 @@
+"""BASELINE.json configs 2, 3 and 4 at FULL size (224x224x160, CFG-W4) under `pytest -m gpu`, against the fp32 CPU
+oracle, plus the error attribution the sampling tolerance rests on.
+
+Stated bf16 tolerances (the reference is fp32 end to end; this path keeps weights and activations in bf16 with fp32
+accumulation, statistics and chain state):
+
+* per-step denoiser output (pred_xstart), against the oracle evaluated ON THE SAME x_t: rel-L2 <= 3e-2 at every step;
+* final sampled volume after IDWT + clamp + mask, against the oracle's own T-step chain with the same noise:
+  PSNR >= 30 dB, SSIM >= 0.99 (11^3 uniform window), max-abs <= 0.5;
+* the chain difference between the two is attributed, step by step, to (a) the error the kernels make in that step
+  (`intrinsic`, the first bullet) and (b) what the fp32 reference network itself does to the difference it inherits
+  (`propagated`: oracle(x_t of this path) - oracle(x_t of the oracle chain), computed entirely on the CPU in fp32).
+
+Why the chain difference grows with the step index although the per-step error does not: x_{t-1} = c1[t] x0_hat +
+c2[t] x_t + sigma[t] z with c1 = 0.016, 0.04, 0.08, 0.16, 0.26, 0.38, 0.53, 0.73, 1.0, 1.0 along the 10 'sampled' steps,
+so the SAME relative error of x0_hat weighs 60x more in the last sample than in the first, and the seeded random
+network amplifies an input difference by ~2-3x per call (measured below with the oracle alone)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import bench
+from oracle import diffusion as od
+from oracle import train as otr
+from oracle import wunet as ow
+from oracle.make_golden import SMALL_CFG
+
+pytestmark = pytest.mark.gpu
+
+T = 10
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def psnr(got, ref, peak=1.0):
+    mse = float(((got.double() - ref.double()) ** 2).mean())
+    return 10.0 * math.log10(peak * peak / max(mse, 1e-30))
+
+
+def ssim3d(a, b, win=11, L=1.0):
+    """Mean SSIM of two (D,H,W) volumes in [0, L], uniform win^3 window, K1 = 0.01, K2 = 0.03."""
+    a, b = a[None, None].double(), b[None, None].double()
+    c1, c2 = (0.01 * L) ** 2, (0.03 * L) ** 2
+    mu_a, mu_b = F.avg_pool3d(a, win, 1), F.avg_pool3d(b, win, 1)
+    va = F.avg_pool3d(a * a, win, 1) - mu_a ** 2
+    vb = F.avg_pool3d(b * b, win, 1) - mu_b ** 2
+    cov = F.avg_pool3d(a * b, win, 1) - mu_a * mu_b
+    return float((((2 * mu_a * mu_b + c1) * (2 * cov + c2)) / ((mu_a ** 2 + mu_b ** 2 + c1) * (va + vb + c2))).mean())
+
+
+@pytest.fixture(scope="module")
+def full_model():
+    torch.set_num_threads(os.cpu_count() or 1)
+    model, diffusion = bench.build_model(torch.device("cuda"))
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    return model, diffusion, sd
+
+
+@pytest.fixture()
+def noise_hook():
+    """Feed the fused sampler pre-drawn per-step noise (indexed by diffusion step) instead of its own Philox draw."""
+    from fcwdm.sampler import FusedSampler
+    box = {}
+
+    def install(per_step):
+        box["n"] = per_step
+        FusedSampler.noise_hook = staticmethod(lambda buf, i: buf.copy_(per_step[i]))
+
+    yield install
+    FusedSampler.noise_hook = None
+
+
+def attributed_chain(model, diffusion, net, x_T, cond_gpu, cond_cpu, noises, label):
+    """Run the fused sampler and the oracle chain with the same noise; per step return
+    (chain rel-L2 of the sample, intrinsic rel-L2 of pred_xstart, propagated rel-L2 of pred_xstart)."""
+    tab = od.Tables(diffusion.betas)
+    tmap = list(diffusion.timestep_map)
+    steps = diffusion.num_timesteps
+    gpu = []
+    with torch.no_grad():
+        for out in diffusion.p_sample_loop_progressive(model, tuple(x_T.shape), time=steps, noise=x_T.cuda(), cond=cond_gpu,
+                                                       progress=False):
+            gpu.append((out["sample"].cpu(), out["pred_xstart"].cpu()))
+    rows = []
+    x_ref, x_gpu = x_T.clone(), x_T.clone()
+    print(f"\n{label}\n| step | t | c1 | chain rel-L2 (sample) | intrinsic rel-L2 (pred_xstart, same x_t) | propagated rel-L2 (fp32 oracle) |\n|---|---|---|---|---|---|")
+    for k, i in enumerate(reversed(range(steps))):
+        t = torch.tensor([i] * x_T.shape[0])
+        with torch.no_grad():
+            ref = od.p_sample(tab, net, x_ref, t, cond=cond_cpu, timestep_map=tmap, noise=noises[i].cpu())
+            if k == 0:
+                restart = ref                                     # both chains start from the same x_T
+            else:
+                restart = od.p_sample(tab, net, x_gpu, t, cond=cond_cpu, timestep_map=tmap, noise=noises[i].cpu())
+        chain = rel(gpu[k][0], ref["sample"])
+        intrinsic = rel(gpu[k][1], restart["pred_xstart"])
+        propagated = rel(restart["pred_xstart"], ref["pred_xstart"])
+        # the fused posterior update is linear: d(sample) = c1 d(pred_xstart) + c2 d(x_t), exactly (fp32)
+        c1, c2 = float(tab.posterior_mean_coef1[i]), float(tab.posterior_mean_coef2[i])
+        lhs = float((gpu[k][0] - ref["sample"]).double().norm())
+        rhs = c1 * float((gpu[k][1] - ref["pred_xstart"]).double().norm()) + c2 * float((x_gpu - x_ref).double().norm())
+        assert lhs <= rhs * (1 + 1e-3) + 1e-5 * float(ref["sample"].double().norm()), (k, lhs, rhs)
+        rows.append((chain, intrinsic, propagated))
+        print(f"| {k} | {i} | {tab.posterior_mean_coef1[i]:.3f} | {chain:.3e} | {intrinsic:.3e} | {propagated:.3e} |", flush=True)
+        x_ref, x_gpu = ref["sample"], gpu[k][0]
+    return gpu, x_ref, rows
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# config 2: full respaced p_sample_loop, batch 1, 224x224x160
+# ----------------------------------------------------------------------------------------------------------------------
+def test_config2_full_size_loop_against_oracle(full_model, noise_hook):
+    """gaussian_diffusion.py:668-719 + scripts/sample.py:100-125 at the BASELINE size, T = 10 'sampled'."""
+    from fcwdm import ops, pipeline
+    model, diffusion, sd = full_model
+    assert diffusion.num_timesteps == T
+    vol, x_T = bench.synth_volume(3)
+    g = torch.Generator().manual_seed(77)
+    noises = [torch.randn(x_T.shape, generator=g).cuda() for _ in range(T)]
+    noise_hook(noises)
+    vd = vol.cuda()
+    cond_gpu = pipeline.build_cond(vd[:, 1:2], vd[:, 2:3], vd[:, 3:4])
+    cond_cpu = torch.cat([od.wavelet_pack(vol[:, k:k + 1]) for k in (1, 2, 3)], dim=1)
+    assert float((cond_gpu.cpu() - cond_cpu).abs().max()) <= 2e-6
+    net = lambda xin, tt: ow.wunet_forward(sd, xin, tt, model_channels=64, channel_mult=(1, 2, 2, 4))
+    gpu, x_ref, rows = attributed_chain(model, diffusion, net, x_T, cond_gpu, cond_cpu, noises, "config 2, full size")
+    for k, (chain, intrinsic, propagated) in enumerate(rows):
+        assert intrinsic <= 3e-2, (k, intrinsic)                  # the kernels' own error never grows along the chain
+    # the chain difference itself is bounded step by step inside attributed_chain (linearity of the posterior update);
+    # its growth is the schedule's c1 ramp times the fp32 network's own response to an input difference (`propagated`)
+    assert rows[0][0] <= 1e-3 and rows[-1][0] <= 0.2, (rows[0], rows[-1])
+    # p_sample_loop (the lean path: in-place state, no per-step clones, no pred_xstart) returns the same final sample
+    with torch.no_grad():
+        final = diffusion.p_sample_loop(model, tuple(x_T.shape), noise=x_T.cuda(), cond=cond_gpu, progress=False)
+    assert rel(final.cpu(), gpu[-1][0]) <= 5e-3
+    img = ops.sample_to_image(final, vd[:, 1:2]).cpu()[0, 0][:, :, :155]
+    ref_img = od.sample_postprocess(x_ref, vol[:, 1:2])[0]
+    mx = float((img - ref_img).abs().max())
+    p, s = psnr(img, ref_img), ssim3d(img, ref_img)
+    print(f"final image {tuple(ref_img.shape)}: max-abs {mx:.3e}, PSNR {p:.1f} dB, SSIM {s:.5f}")
+    assert p >= 30.0 and s >= 0.99 and mx <= 0.5
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# config 3: 8 volumes per GPU
+# ----------------------------------------------------------------------------------------------------------------------
+def test_config3_batch8_equals_batch1(full_model, noise_hook):
+    """Every volume of a batch of 8 is the volume a batch of 1 produces from the same noise and conditioning (the
+    statistics of GroupNorm32 are per sample; nothing else couples the batch)."""
+    from fcwdm import pipeline
+    model, diffusion, _ = full_model
+    B = 8
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(5)
+    vol = torch.rand((B, 4) + bench.IMAGE, device=dev, generator=g)
+    vol[:, :, :8] = 0
+    x_T = torch.randn((B, 8) + bench.LATENT, device=dev, generator=g)
+    noises = [torch.randn((B, 8) + bench.LATENT, device=dev, generator=g) for _ in range(T)]
+    noise_hook(noises)
+    img8 = pipeline.synthesize(diffusion, model, vol[:, 1:2], vol[:, 2:3], vol[:, 3:4], x_T)
+    assert img8.shape == (B,) + bench.IMAGE[:2] + (155,) and bool(torch.isfinite(img8).all())
+    for j in (0, 5):
+        noise_hook([n[j:j + 1] for n in noises])
+        img1 = pipeline.synthesize(diffusion, model, vol[j:j + 1, 1:2], vol[j:j + 1, 2:3], vol[j:j + 1, 3:4], x_T[j:j + 1])
+        r, p = rel(img8[j:j + 1], img1), psnr(img8[j:j + 1], img1)
+        print(f"batch-8 volume {j} vs batch-1: rel-L2 {r:.3e}, PSNR {p:.1f} dB, max-abs {float((img8[j:j + 1] - img1).abs().max()):.3e}")
+        # same kernels on the same values; the only differences are atomic summation order in the GroupNorm statistics
+        # and fused-vs-separate statistics passes at the low resolutions, amplified along the 10-step chain
+        assert r <= 3e-2 and p >= 40.0
+    # different volumes do differ (the comparison above is not vacuous)
+    assert rel(img8[1:2], img8[0:1]) > 0.1
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# config 4: one training step at full size
+# ----------------------------------------------------------------------------------------------------------------------
+def test_config4_full_size_training_step_against_oracle(full_model):
+    """training_losses -> backward at 1 x 4 x 224x224x160 (train_util.py:396-460) against the oracle's fp32 CPU autograd:
+    loss within 1e-2 relative, per-parameter gradient rel-L2 <= 8e-2 / cosine >= 0.995, all parameters <= 4e-2."""
+    from test_train_gpu import compare_grads, run_training_losses
+    model, diffusion, sd = full_model
+    model.train()
+    try:
+        gen = torch.Generator().manual_seed(8)
+        batch = {k: torch.rand((1, 1) + bench.IMAGE, generator=gen) for k in ("t1n", "t1c", "t2w", "t2f")}
+        t = torch.tensor([6])
+        noise = torch.randn((1, 1) + bench.IMAGE, generator=gen)
+        for p in model.parameters():
+            p.grad = None
+        loss, terms, mo = run_training_losses(diffusion, model, batch, t, noise)
+        loss.backward()
+        torch.cuda.synchronize()
+        tied = ow.tie_output_blocks(dict(sd), 4)
+        ref_loss, ref_terms, ref_out, ref_grads = otr.training_step_grads(
+            tied, od.Tables(diffusion.betas), batch, t, noise, model_channels=64, channel_mult=(1, 2, 2, 4),
+            timestep_map=list(diffusion.timestep_map))
+        print(f"full-size training step: loss {float(loss):.6f} vs oracle {float(ref_loss):.6f}; "
+              f"model output rel-L2 {rel(mo.detach().cpu(), ref_out):.3e}")
+        assert abs(float(loss) - float(ref_loss)) <= 1e-2 * float(ref_loss)
+        np.testing.assert_allclose(terms["mse_wav"].detach().cpu().numpy(), ref_terms.numpy(), rtol=2e-2)
+        params = dict(model.named_parameters())
+        norms = {n: float(ref_grads[n].double().norm()) for n in params}
+        compare_grads({n: p.grad for n, p in params.items()}, lambda n: ref_grads[n], norms, "oracle (CFG-W4 full size)")
+    finally:
+        for p in model.parameters():
+            p.grad = None
+        model.eval()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# error attribution on the small model: random (non-contractive) vs contractive weights, and a T = 100 chain
+# ----------------------------------------------------------------------------------------------------------------------
+def _small(scale_out=1.0):
+    from guided_diffusion.wunet import WavUNetModel
+    m = WavUNetModel(**SMALL_CFG)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = ow.tie_output_blocks(ow.seeded_state_dict(shapes, seed=0), len(SMALL_CFG["channel_mult"]))
+    if scale_out != 1.0:                  # shrink the network's response to x_t: the denoiser becomes a contraction
+        sd = dict(sd)
+        sd["out.2.weight"] = sd["out.2.weight"] * scale_out
+    m.load_state_dict(sd, strict=True)
+    m.to("cuda").eval()
+    net = lambda xin, tt: ow.wunet_forward(sd, xin, tt, model_channels=SMALL_CFG["model_channels"],
+                                           channel_mult=SMALL_CFG["channel_mult"], num_res_blocks=SMALL_CFG["num_res_blocks"],
+                                           num_groups=SMALL_CFG["num_groups"])
+    return m, net
+
+
+@pytest.mark.parametrize("steps,respacing", [(10, ""), (1000, "100")])
+def test_error_growth_is_the_networks_not_the_kernels(noise_hook, steps, respacing):
+    """The same chain with the seeded random weights and with the output conv scaled by 0.05 (a contractive denoiser).
+    In both the kernels' per-step error stays within the single-call tolerance; only the random network's chain
+    difference grows, and it does so in the fp32 oracle alone (`propagated`).  With respacing '100' this is the T = 100
+    configuration of SURVEY.md section 8d on a 16^3 latent."""
+    from guided_diffusion.script_util import create_gaussian_diffusion
+    g = torch.Generator().manual_seed(21)
+    x_T = torch.randn(1, 8, 16, 16, 16, generator=g)
+    cond = torch.rand(1, 24, 16, 16, 16, generator=g)
+    final = {}
+    for name, scale in (("random", 1.0), ("contractive", 0.05)):
+        m, net = _small(scale)
+        if respacing:
+            d = create_gaussian_diffusion(steps=steps, predict_xstart=True, timestep_respacing=respacing, mode="i2i")
+        else:
+            d = create_gaussian_diffusion(steps=steps, predict_xstart=True, sample_schedule="sampled", mode="i2i")
+        n = d.num_timesteps
+        noises = [torch.randn(x_T.shape, generator=g).cuda() for _ in range(n)]
+        noise_hook(noises)
+        _, _, rows = attributed_chain(m, d, net, x_T, cond.cuda(), cond, noises, f"small model, {name} weights, T = {n}")
+        worst_intrinsic = max(r[1] for r in rows)
+        final[name] = (rows[-1][0], worst_intrinsic, max(r[2] for r in rows))
+        assert worst_intrinsic <= 3e-2, (name, worst_intrinsic)
+    print({k: tuple(f"{v:.3e}" for v in vals) for k, vals in final.items()})
+    # contractive network: the chain ends no further from the reference than a few single-call errors
+    assert final["contractive"][0] <= 4 * final["contractive"][1] + 1e-4
+    assert final["contractive"][0] <= 3e-2
