@@ -1,0 +1,66 @@
+// GroupNorm helpers shared by the conv3d kernels' epilogues / operand transforms (conv3d.cu, conv3d_chain.cu).
+#pragma once
+#include "common.cuh"
+
+namespace fcwdm {
+
+// ---- fused GroupNorm statistics (epilogue) ----------------------------------------------------------
+// Reduce V per-lane values across the 32 lanes of a warp with a halving butterfly (lane pairs exchange HALF of their
+// values per step: V/2 + V/4 + ... + 1 shuffles, then log2(32/V) full steps) and add value i into dst[i].
+// 9 shuffles for V = 8 instead of 40 with one full butterfly per value.
+template <int N, int OFF>
+__device__ __forceinline__ void halve_step(float* a, int lane) {
+    const bool upper = (lane & OFF) != 0;
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const float send = upper ? a[i] : a[i + N / 2];
+        const float keep = upper ? a[i + N / 2] : a[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+    }
+}
+template <int V>
+__device__ __forceinline__ void warp_reduce_scatter(float* a, int lane, float* dst) {
+    static_assert(V == 2 || V == 4 || V == 8 || V == 16, "unsupported value count");
+    if constexpr (V == 16) { halve_step<16, 16>(a, lane); halve_step<8, 8>(a, lane); halve_step<4, 4>(a, lane); halve_step<2, 2>(a, lane); }
+    if constexpr (V == 8) { halve_step<8, 16>(a, lane); halve_step<4, 8>(a, lane); halve_step<2, 4>(a, lane); }
+    if constexpr (V == 4) { halve_step<4, 16>(a, lane); halve_step<2, 8>(a, lane); }
+    if constexpr (V == 2) { halve_step<2, 16>(a, lane); }
+#pragma unroll
+    for (int off = 16 / V; off > 0; off >>= 1) a[0] += __shfl_xor_sync(0xffffffffu, a[0], off);
+    if ((lane & (32 / V - 1)) == 0) dst[lane / (32 / V)] += a[0];
+}
+// vr: the 8 consecutive output channels [co, co+8) of this lane's voxel; CPG channels per group (CPG <= 4 here)
+template <int CPG>
+__device__ __forceinline__ void gn_accumulate(const float* vr, float* my_stat, int co, int lane) {
+    constexpr int V = 2 * (8 / CPG);
+    float a[V];
+#pragma unroll
+    for (int g = 0; g < 8 / CPG; ++g) {
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int e = 0; e < CPG; ++e) {
+            s += vr[g * CPG + e];
+            q = fmaf(vr[g * CPG + e], vr[g * CPG + e], q);
+        }
+        a[2 * g] = s;
+        a[2 * g + 1] = q;
+    }
+    warp_reduce_scatter<V>(a, lane, my_stat + 2 * (co / CPG));
+}
+// CPG >= 8: the whole 8-channel run belongs to one group
+__device__ __forceinline__ void gn_accumulate_wide(const float* vr, float* my_stat, int grp, int lane) {
+    float a[2] = {0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        a[0] += vr[e];
+        a[1] = fmaf(vr[e], vr[e], a[1]);
+    }
+    warp_reduce_scatter<2>(a, lane, my_stat + 2 * grp);
+}
+__device__ __forceinline__ float c_silu(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return x * fmaf(0.5f, t, 0.5f);
+}
+
+}  // namespace fcwdm

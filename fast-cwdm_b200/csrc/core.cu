@@ -19,6 +19,7 @@ void set_error(const char* fmt, ...) {
 int conv3d_init_device();       // conv3d.cu
 int conv3d_pair_init_device();  // conv3d_pair.cu
 int conv3d_wgrad_init_device(); // conv3d_wgrad.cu
+int conv3d_chain_init_device(); // conv3d_chain.cu
 
 bool pdl_enabled() {
     static int v = -1;
@@ -49,5 +50,7 @@ extern "C" int fcwdm_init(int device) {
     if (rc) return rc;
     rc = fcwdm::conv3d_pair_init_device();
     if (rc) return rc;
-    return fcwdm::conv3d_wgrad_init_device();
+    rc = fcwdm::conv3d_wgrad_init_device();
+    if (rc) return rc;
+    return fcwdm::conv3d_chain_init_device();
 }

@@ -19,7 +19,7 @@ INCLUDE = os.path.join(ROOT, "include")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libfcwdm.so")
 
-SOURCES = ["core.cu", "haar.cu", "diffusion.cu", "norm.cu", "linear.cu", "conv3d.cu", "conv3d_pair.cu", "conv3d_wgrad.cu", "train.cu", "resample.cu", "preprocess.cu"]
+SOURCES = ["core.cu", "haar.cu", "diffusion.cu", "norm.cu", "linear.cu", "conv3d.cu", "conv3d_pair.cu", "conv3d_chain.cu", "conv3d_wgrad.cu", "train.cu", "resample.cu", "preprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 if os.environ.get("FCWDM_CONV_TRACE") == "1":          # development build with in-kernel clock stamps (tools/conv_trace.py)

@@ -60,6 +60,12 @@ class WavUNetEngine:
         self.use_pair = os.environ.get("FCWDM_NO_PAIR", "0") != "1"
         self.fuse_gn_in = os.environ.get("FCWDM_NO_FUSED_GN_IN", "0") != "1"
         self.fuse_gn_in_general = os.environ.get("FCWDM_NO_FUSED_GN_IN_GENERAL", "0") != "1"   # single-CTA kernel too
+        # runs of consecutive low-resolution convs (<= chain_rows voxels per launch) go out as ONE persistent launch
+        # (csrc/conv3d_chain.cu); only the plain inference engine defers launches, the subclasses interleave other kernels
+        self.use_chain = type(self) is WavUNetEngine and os.environ.get("FCWDM_NO_CHAIN", "0") != "1"
+        self.chain_rows = int(os.environ.get("FCWDM_CHAIN_ROWS", "20000"))
+        self._chain = []
+        self.chain_launches = 0
 
     # ------------------------------------------------------------------ weights
     def _signature(self):
@@ -182,6 +188,13 @@ class WavUNetEngine:
         if stats_groups and stats_groups <= 32 and (ok_pair or ok_single):
             stats = self._stats_slot(N, stats_groups, x.device)
             self._stats[id(y)] = (stats, stats_groups, y)     # holding y keeps its id unique until consumed
+        if self._chainable(pk, rows, x, gn_in):
+            # deferred: becomes one layer of the next fcwdm_conv3d_chain launch (flushed before any other kernel runs)
+            self._chain.append(ops.conv3d_chain_layer(x, pk.wp, pk.bias, y, (N,) + tuple(dims), pk.cin, pk.cout,
+                                                      chan_bias=chan_bias, residual=residual, gn_stats=stats,
+                                                      gn_groups=stats_groups if stats is not None else 0, gn_in=gn_in))
+            return y
+        self._flush_chain()
         if pk.pair:
             ops.conv3d_pair_cl(x, pk.wp, pk.bias, y, (N,) + tuple(dims), pk.cin, pk.cout, chan_bias=chan_bias,
                                residual=residual, gn_stats=stats, gn_groups=stats_groups if stats is not None else 0,
@@ -191,6 +204,29 @@ class WavUNetEngine:
                           residual=residual, gn_stats=stats, gn_groups=stats_groups if stats is not None else 0,
                           gn_in=gn_in)
         return y
+
+    def _chainable(self, pk, rows, x, gn_in):
+        if not self.use_chain or pk.pair or pk.k != 3 or rows > self.chain_rows:
+            return False
+        if not ops.conv3d_chain_supported(pk.cin, pk.cout, 3) or x.stride(0) < pk.cin:
+            return False
+        return gn_in is None or pk.cin <= 256
+
+    def _flush_chain(self):
+        """Launch the deferred run of low-resolution convs (if any) as persistent chain launches."""
+        if not self._chain:
+            return
+        pending, self._chain = self._chain, []
+        cap = native.load().fcwdm_conv3d_chain_max_layers()
+        for i in range(0, len(pending), cap):
+            part = pending[i:i + cap]
+            if self._arena is None or self._arena_pos + 1 > self._arena.numel():
+                self._arena = torch.zeros(1 << 18, dtype=torch.float64, device=part[0][1][0].device)
+                self._arena_pos = 0
+            counter = self._arena[self._arena_pos:self._arena_pos + 1]      # 8 zero bytes: the grid-barrier counter
+            self._arena_pos += 1
+            ops.conv3d_chain([layer for layer, _ in part], counter)
+            self.chain_launches += 1
 
     def _stats_slot(self, N, G, device):
         """Slice of the per-forward statistics arena (zeroed by ONE memset at the start of forward_cl)."""
@@ -211,6 +247,7 @@ class WavUNetEngine:
 
     def _gn_silu(self, gn, x, N, S, silu=True):
         C = gn.num_channels
+        self._flush_chain()
         y = self._buf(N * S, C, x.device)
         stats, have = self._take_stats(gn, x, N)
         ops.groupnorm_silu(x, y, stats, self._p32(gn.weight), self._p32(gn.bias), N, S, C, gn.num_groups, gn.eps, silu,
@@ -226,6 +263,7 @@ class WavUNetEngine:
         if fusable and self.fuse_gn_in and gn.num_channels == pk.cin and pk.cin % gn.num_groups == 0:
             stats, have = self._take_stats(gn, x, N)
             if not have:
+                self._flush_chain()
                 ops.groupnorm_stats(x, stats, N, S, pk.cin, gn.num_groups)
             return self._conv3d(mod, x, N, dims, gn_in=(stats, self._p32(gn.weight), self._p32(gn.bias),
                                                          gn.num_groups, gn.eps), **kw)
@@ -252,6 +290,7 @@ class WavUNetEngine:
         skip_out = skip
         if blk.down:
             h_full = self._gn_silu_conv(gn1, x, conv1, N, dims)
+            self._flush_chain()
             d2 = (dims[0] // 2, dims[1] // 2, dims[2] // 2)
             s2 = d2[0] * d2[1] * d2[2]
             h = self._buf(N * s2, cout, dev)
@@ -266,6 +305,7 @@ class WavUNetEngine:
             if skip is None:
                 raise FcwdmError("up-sampling ResBlock reached without stored high-frequency sub-bands")
             h_low = self._gn_silu_conv(gn1, x, conv1, N, dims)
+            self._flush_chain()
             d2 = (dims[0] * 2, dims[1] * 2, dims[2] * 2)
             s2 = d2[0] * d2[1] * d2[2]
             h = self._buf(N * s2, cout, dev)
@@ -293,6 +333,7 @@ class WavUNetEngine:
         C = gn.num_channels
         if emb_out.shape[1] != 2 * C:
             raise FcwdmError(f"scale-shift norm: emb_layers must produce 2 x {C} values, got {emb_out.shape[1]}")
+        self._flush_chain()
         y = self._buf(N * S, C, x.device)
         stats, have = self._take_stats(gn, x, N)
         if not have:
@@ -330,6 +371,7 @@ class WavUNetEngine:
                 raise FcwdmError(f"spatial size {tuple(dims)} is not divisible by 2^{levels} (one Haar level per "
                                  f"channel_mult entry; the reference fails the same way, SURVEY.md fact 3)")
         self._stats.clear()
+        self._chain = []
         self._arena = torch.zeros(1 << 18, dtype=torch.float64, device=x_cl.device)   # one memset per forward
         self._arena_pos = 0
         emb = self._emb_all(self.time_embedding(t))
@@ -343,6 +385,7 @@ class WavUNetEngine:
                 d2 = (pyr_dims[0] // 2, pyr_dims[1] // 2, pyr_dims[2] // 2)
                 s2 = d2[0] * d2[1] * d2[2]
                 cat = self._buf(N * s2, 8 * pyr_c, x_cl.device)
+                self._flush_chain()
                 ops.dwt3d_cl(pyramid, (N,) + pyr_dims, pyr_c, cat[:, :pyr_c], cat[:, pyr_c:], lll_scale=1.0 / 3.0,
                              hi_scale=1.0 / 3.0, hi_sb=pyr_c)
                 pyramid = self._conv3d(first.conv, cat, N, d2, residual=h, stats_groups=m.num_groups)
@@ -372,8 +415,10 @@ class WavUNetEngine:
         for module in m.out_res:
             for layer in module:
                 h, _, hdims = self._resblock(layer, h, None, emb, N, hdims)
-        return self._gn_silu_conv(m.out[0], h, m.out[2], N, hdims,
-                                  out_ld=out_ld or max(8, (m.out_channels + 7) // 8 * 8))
+        out = self._gn_silu_conv(m.out[0], h, m.out[2], N, hdims,
+                                 out_ld=out_ld or max(8, (m.out_channels + 7) // 8 * 8))
+        self._flush_chain()
+        return out
 
     def forward(self, x, timesteps):
         """Planar fp32 API of the reference: x (N, C, D, H, W), timesteps (N,) -> (N, out_channels, D, H, W)."""

@@ -16,6 +16,15 @@ _c_p = ctypes.c_void_p
 _c_f = ctypes.c_float
 _c_int = ctypes.c_int
 
+class ChainLayer(ctypes.Structure):
+    """fcwdm_chain_layer of include/fcwdm.h: one layer of a fcwdm_conv3d_chain launch."""
+    _fields_ = [("x", _c_p), ("x_ld", _c_i64), ("wp", _c_p), ("bias", _c_p), ("chan_bias", _c_p), ("cb_ld", _c_i64),
+                ("residual", _c_p), ("res_ld", _c_i64), ("y", _c_p), ("y_ld", _c_i64), ("gn_stats", _c_p),
+                ("gn_groups", _c_i64), ("gn_in_stats", _c_p), ("gn_in_gamma", _c_p), ("gn_in_beta", _c_p),
+                ("gn_in_groups", _c_i64), ("gn_in_eps", _c_f), ("N", _c_i64), ("D", _c_i64), ("H", _c_i64), ("W", _c_i64),
+                ("Cin", _c_i64), ("Cout", _c_i64)]
+
+
 # name -> (restype, argtypes); mirrors include/fcwdm.h one to one
 PROTOTYPES = {
     "fcwdm_version": (_c_int, []),
@@ -70,6 +79,9 @@ PROTOTYPES = {
     "fcwdm_clip_normalize_workspace_bytes": (_c_i64, [_c_i64]),
     "fcwdm_clip_normalize": (_c_int, [_c_p, _c_p, _c_p, _c_p, _c_i64] + [_c_i64] * 7 + [ctypes.c_double, ctypes.c_double, _c_p]),
     "fcwdm_debug_set_conv_trace": (_c_int, [_c_p]),
+    "fcwdm_conv3d_chain_supported": (_c_int, [_c_i64, _c_i64, _c_int]),
+    "fcwdm_conv3d_chain_max_layers": (_c_int, []),
+    "fcwdm_conv3d_chain": (_c_int, [ctypes.POINTER(ChainLayer), _c_i64, _c_p, _c_p]),
 }
 
 FCWDM_F32, FCWDM_BF16 = 0, 1

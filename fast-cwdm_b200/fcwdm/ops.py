@@ -258,6 +258,39 @@ def conv3d_cl(x, wp, bias, y, dims, cin, cout, k, chan_bias=None, residual=None,
                     N, D, H, W, cin, cout, k, st)
 
 
+def conv3d_chain_supported(cin, cout, k):
+    return bool(native.load().fcwdm_conv3d_chain_supported(cin, cout, k))
+
+
+def conv3d_chain_layer(x, wp, bias, y, dims, cin, cout, chan_bias=None, residual=None, gn_stats=None, gn_groups=0, gn_in=None):
+    """Describe one layer of a conv3d_chain launch (same arguments as conv3d_cl, k = 3).  Returns (struct, keep-alive)."""
+    N, D, H, W = dims
+    L = native.ChainLayer()
+    L.x, L.x_ld, L.wp = x.data_ptr(), x.stride(0), wp.data_ptr()
+    L.bias = bias.data_ptr() if bias is not None else None
+    L.chan_bias = chan_bias.data_ptr() if chan_bias is not None else None
+    L.cb_ld = chan_bias.stride(0) if chan_bias is not None else 0
+    L.residual = residual.data_ptr() if residual is not None else None
+    L.res_ld = residual.stride(0) if residual is not None else 0
+    L.y, L.y_ld = y.data_ptr(), y.stride(0)
+    L.gn_stats = gn_stats.data_ptr() if gn_stats is not None else None
+    L.gn_groups = gn_groups if gn_stats is not None else 0
+    if gn_in is not None:
+        L.gn_in_stats, L.gn_in_gamma, L.gn_in_beta = gn_in[0].data_ptr(), gn_in[1].data_ptr(), gn_in[2].data_ptr()
+        L.gn_in_groups, L.gn_in_eps = gn_in[3], float(gn_in[4])
+    L.N, L.D, L.H, L.W, L.Cin, L.Cout = N, D, H, W, cin, cout
+    return L, (x, wp, bias, y, chan_bias, residual, gn_stats, gn_in)
+
+
+def conv3d_chain(layers, sync_counter):
+    """Run a list of conv3d_chain_layer structs as ONE persistent launch (csrc/conv3d_chain.cu).  sync_counter: a device
+    tensor whose first 4 bytes are zero (the grid-barrier counter)."""
+    n = len(layers)
+    arr = (native.ChainLayer * n)(*layers)
+    with _on(sync_counter.device) as st:
+        native.call("fcwdm_conv3d_chain", arr, n, _ptr(sync_counter), st)
+
+
 def conv3d_pair_supported(cin, cout, k):
     return bool(native.load().fcwdm_conv3d_pair_supported(cin, cout, k))
 

@@ -117,9 +117,9 @@ class TrainLoop:
         from fcwdm.optim import FusedAdamW
         self.opt = FusedAdamW(self.model, lr=self.lr, weight_decay=self.weight_decay)
         self.grad_sync = ddp.attach(self.model) if _world() > 1 else None
-        if self.resume_step:
+        if self.resume_step or self.resume_checkpoint or find_resume_checkpoint():
             logger.log(f"Resume Step: {self.resume_step}")
-            self._load_optimizer_state()
+            self._load_optimizer_state()         # also for a BEST file resumed at step 0 (the reference skips it then)
         self._ones = th.ones(8, device=self.device)
         self._nonfinite = th.zeros((), dtype=th.bool, device=self.device)
         self.last_info = {}

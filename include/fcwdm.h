@@ -189,6 +189,41 @@ int fcwdm_conv3d_gn_fwd(const void* x, int64_t x_ld, const void* wp, const float
                         int64_t Cout, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * K5c: a RUN of consecutive low-resolution 3x3x3 convolutions in ONE persistent launch (csrc/conv3d_chain.cu): the
+ * layers of WavUNetModel at 28x28x20 voxels and below (wunet.py:533-609,615-675), where one layer has fewer output
+ * tiles than the GPU has SMs and launch / fill / drain latency, not arithmetic, sets its time.  Layer l+1 may read
+ * (as input, residual or GroupNorm statistics) anything layers <= l wrote: layers are separated by grid barriers.
+ * Every layer is an fcwdm_conv3d_fwd / fcwdm_conv3d_gn_fwd with the same operand meaning (gn_in_stats == NULL: plain
+ * input); C_in a multiple of 64, C_out a multiple of 128, weights packed by fcwdm_conv3d_pack_weights.
+ * sync_counter: 4 bytes of device memory, ZERO at launch (the grid-barrier counter; left non-zero).
+ * The launch needs every CTA co-resident (one per SM, clusters of 4): call it on a stream whose GPU it does not share
+ * with another concurrently running fcwdm_conv3d_chain.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct fcwdm_chain_layer {
+    const void* x;
+    int64_t x_ld;
+    const void* wp;
+    const float* bias;
+    const float* chan_bias;
+    int64_t cb_ld;
+    const void* residual;
+    int64_t res_ld;
+    void* y;
+    int64_t y_ld;
+    double* gn_stats;
+    int64_t gn_groups;
+    const double* gn_in_stats;
+    const float* gn_in_gamma;
+    const float* gn_in_beta;
+    int64_t gn_in_groups;
+    float gn_in_eps;
+    int64_t N, D, H, W, Cin, Cout;
+} fcwdm_chain_layer;
+int fcwdm_conv3d_chain_supported(int64_t Cin, int64_t Cout, int ksize);
+int fcwdm_conv3d_chain_max_layers(void);
+int fcwdm_conv3d_chain(const fcwdm_chain_layer* layers, int64_t n_layers, void* sync_counter, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * K5b: the same 3x3x3 convolution for C_in <= 64 and C_out <= 64 (the full-resolution layers) as a kd-fused,
  * two-CTA (cta_group::2) implicit GEMM with the weights resident in the CTA pair's shared memory
  * (csrc/conv3d_pair.cu).  Same semantics and epilogue options as fcwdm_conv3d_fwd; its own weight packing

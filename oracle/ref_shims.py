@@ -59,6 +59,16 @@ def stage_reference(src="/root/reference"):
             if not os.path.exists(d) or open(d, "rb").read() != data:
                 shutil.copyfile(s, d)
             manifest[f"{pkg}/{name}"] = {"bytes": len(data), "sha256": hashlib.sha256(data).hexdigest()}
+    # the two entry scripts the drop-in claims to serve unchanged (tests/test_reference_scripts_gpu.py executes them)
+    os.makedirs(os.path.join(STAGED_ROOT, "scripts"), exist_ok=True)
+    for name in ("sample.py", "train.py"):
+        s = os.path.join(src, "scripts", name)
+        if os.path.exists(s):
+            data = open(s, "rb").read()
+            d = os.path.join(STAGED_ROOT, "scripts", name)
+            if not os.path.exists(d) or open(d, "rb").read() != data:
+                shutil.copyfile(s, d)
+            manifest[f"scripts/{name}"] = {"bytes": len(data), "sha256": hashlib.sha256(data).hexdigest()}
     with open(os.path.join(STAGED_ROOT, "MANIFEST.json"), "w") as fh:
         json.dump({"source": src, "files": manifest}, fh, indent=1, sort_keys=True)
     return STAGED_ROOT
@@ -70,6 +80,15 @@ _HAAR = dict(dec_lo=[_S, _S], dec_hi=[-_S, _S], rec_lo=[_S, _S], rec_hi=[_S, -_S
 
 def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "guided_diffusion"))
+
+
+def reference_script(name):
+    """Path of the reference's unmodified scripts/<name> (mount or staged copy), or None."""
+    for root in (REFERENCE_ROOT, STAGED_ROOT):
+        p = os.path.join(root, "scripts", name)
+        if os.path.exists(p):
+            return p
+    return None
 
 
 def _install_stubs():

@@ -112,17 +112,41 @@ def test_trainloop_matches_hand_written_steps_and_checkpoints(tmp_path, monkeypa
         sd = torch.load(best, map_location="cpu")
         assert list(sd) == list(m1.state_dict())                       # the reference's key names, loadable as-is
 
-        # ---- resume: weights come back, the step counter is parsed from the file name, optimizer state is reloaded
+        # ---- resume from the BEST file: weights and optimizer state come back; its name carries no step field
+        # ("..._BEST_sampled_10.pt": the reference's parser would read the diffusion step count 10 as the step), so the
+        # caller's resume_step stands
         m3 = fresh_model(seed=3)
         loop3 = make_loop(m3, d10, 0, resume_checkpoint=str(best))
-        assert loop3.resume_step == 10                                   # "..._sampled_10.pt" -> 10, as in the reference
+        assert loop3.resume_step == 0
         for k, v in m3.state_dict().items():
             assert torch.equal(v.cpu(), sd[k]), k
-        assert loop3.opt.step_count == torch.load(ck / "opt_best_t1n.pt", map_location="cpu")["step"]
+        opt_sd = torch.load(ck / "opt_best_t1n.pt", map_location="cpu")
+        assert set(opt_sd) == {"state", "param_groups"}                  # torch.optim.AdamW's layout (train_util.py:75-82)
+        assert loop3.opt.step_count == int(opt_sd["state"][0]["step"]) > 0
         assert loop3.best_losses == {"t1n": float(table["t1n"])}
+        # the same file loads into the reference's optimizer class, and that optimizer's state loads back
+        ref_opt = torch.optim.AdamW(m3.parameters(), lr=1e-3, weight_decay=0.0)
+        ref_opt.load_state_dict(torch.load(ck / "opt_best_t1n.pt", map_location="cuda"))
+        back = ref_opt.state_dict()
+        loop3.opt.load_state_dict(back)
+        assert loop3.opt.step_count == int(opt_sd["state"][0]["step"])
+        lo, hi = loop3.opt.offsets[5]
+        assert torch.equal(loop3.opt.m[lo:hi].cpu().reshape(-1), opt_sd["state"][5]["exp_avg"].reshape(-1))
+        with pytest.raises(ValueError):
+            loop3.opt.load_state_dict({"state": {}, "param_groups": [{"params": [0, 1]}]})
+
+        # ---- save -> resume round trip of the step-numbered checkpoint: same step, same moments
+        loop3.step = 7
         loop3.save()
-        assert (ck / f"brats_t1n_{loop3.step + 10:06d}_sampled_10.pt").exists()
-        assert (ck / f"opt{loop3.step + 10:06d}.pt").exists()
+        numbered = ck / "brats_t1n_000007_sampled_10.pt"
+        assert numbered.exists() and (ck / "opt000007.pt").exists()
+        m4 = fresh_model(seed=4)
+        loop4 = make_loop(m4, d10, 0, resume_checkpoint=str(numbered))
+        assert loop4.resume_step == 7                                    # the 6-digit field, not the trailing "_10"
+        assert loop4.opt.step_count == loop3.opt.step_count
+        assert torch.equal(loop4.opt.m, loop3.opt.m) and torch.equal(loop4.opt.v, loop3.opt.v)
+        for (n3, p3), (n4, p4) in zip(m3.named_parameters(), m4.named_parameters()):
+            assert torch.equal(p3, p4), n3
     finally:
         logger.reset()
 
