@@ -62,6 +62,7 @@ struct ChainParams {
     ChainLayer layers[kChainMaxLayers];
     int n_layers;
     int cluster;             // CTAs per cluster of this launch (2 or 4)
+    long long* trace;        // development (-DFCWDM_CONV_TRACE): [grid][kChainMaxLayers][16] %globaltimer stamps, else null
     unsigned int* sync;      // grid-barrier counter, zero at launch; layer l is complete when it reaches (l+1) * gridDim.x
 };
 static_assert(sizeof(ChainParams) <= 32000, "kernel parameters exceed the 32 KB limit of CUDA >= 12.1");
@@ -75,7 +76,11 @@ struct ChainCfg {
     static constexpr int B_TAP_BYTES = N_TILE * 128;
     static constexpr int B_BYTES = 3 * B_TAP_BYTES;               // the 3 kw taps of one (kd, kh)
     static constexpr int B_STAGES = 2;
-    static constexpr int RECV_BYTES = 3 * 32 * 128 * 4;           // s = 4: 3 senders x 32 columns x 128 rows fp32 (s = 2: 1 x 64)
+    // receive slots of the reduce-scatter: [sender][128 rows][CW + 4] fp32 (the 4-float pad keeps 128-bit row accesses
+    // conflict-free); s = 4: 3 x 128 x 36, s = 2: 1 x 128 x 68
+    static constexpr int RECV_BYTES = 3 * 128 * 36 * 4;
+    static constexpr int XF_WARPS = 8, XF_THREADS = XF_WARPS * 32;   // operand hand-over / GroupNorm transform warps
+    static constexpr int THREADS = 256 + XF_THREADS;
     static constexpr int TAIL_BYTES = 4608;                       // barriers | bias | statistics | GN scale/shift
     static constexpr int ACC_STAGES = 2;
     static constexpr int TMEM_COLS = 256;
@@ -150,9 +155,24 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) {
     return r;
 }
 
+// %globaltimer stamps per (CTA, layer), compiled in only with -DFCWDM_CONV_TRACE (tools/chain_trace.py):
+//  0 A producer reaches the layer | 1 grid barrier passed | 2 sgn table ready (transform warps) | 3 first plane landed
+//  4 first plane handed to the MMA | 5 first MMA issued | 6 last MMA issued | 7 accumulator complete (epilogue)
+//  8 partial sums exchanged | 9 tile stored | 10 statistics flushed | 11 arrived at the next grid barrier
+#ifdef FCWDM_CONV_TRACE
+__device__ __forceinline__ long long chain_now() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define CHAIN_TRACE(li, slot) do { if (P.trace != nullptr) P.trace[((size_t)blockIdx.x * kChainMaxLayers + (li)) * 16 + (slot)] = chain_now(); } while (0)
+#else
+#define CHAIN_TRACE(li, slot) do { } while (0)
+#endif
+
 constexpr int kCWarpProdA = 4, kCWarpProdB = 5, kCWarpAlloc = 6, kCWarpMma = 7;
 
-__global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_constant__ ChainParams P) {
+__global__ void __launch_bounds__(ChainCfg::THREADS, 1) conv3d_chain_kernel(const __grid_constant__ ChainParams P) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     using Cfg = ChainCfg;
     constexpr int N_TILE = Cfg::N_TILE;
@@ -176,6 +196,7 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
     float* sbias = reinterpret_cast<float*>(smem_raw + (bars + 1024 - smem_u32(smem_raw)));   // [N_TILE]
     float* wstat = reinterpret_cast<float*>(smem_raw + (bars + 1536 - smem_u32(smem_raw)));   // [4 warps][32 groups][2]
     float* sgn = reinterpret_cast<float*>(smem_raw + (bars + 2560 - smem_u32(smem_raw)));     // [2][256] GN scale / shift
+    float* gstat = reinterpret_cast<float*>(smem_raw + (bars + 512 - smem_u32(smem_raw)));    // [2][64] group mean / rstd
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -184,7 +205,7 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::A_SLOTS; ++i) {
-            mbar_init(full_a + 8 * i, 4);        // the four transform warps hand every plane over
+            mbar_init(full_a + 8 * i, Cfg::XF_WARPS);   // the transform warps hand every plane over
             mbar_init(empty_a + 8 * i, 1);
             mbar_init(landed_a + 8 * i, 1);
         }
@@ -196,7 +217,7 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
             mbar_init(tmem_full + 8 * i, 1);
             mbar_init(tmem_empty + 8 * i, 4);
         }
-        for (int i = 0; i < 3; ++i) mbar_init(ready + 8 * i, 4);   // the four epilogue warps of ONE sender
+        for (int i = 0; i < 3; ++i) mbar_init(ready + 8 * i, 1);   // the receiver's expect_tx; the senders' st.async complete the bytes
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -214,10 +235,12 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
             uint32_t q = 0;
             for (int li = 0; li < P.n_layers; ++li) {
                 const ChainLayer& L = P.layers[li];
+                CHAIN_TRACE(li, 0);
                 if (li > 0) {
                     grid_wait(P.sync, (unsigned int)li * G);          // the previous layer's output is complete everywhere
                     asm volatile("fence.proxy.async.global;" ::: "memory");   // ... and visible to the TMA (async proxy) reads
                 }
+                CHAIN_TRACE(li, 1);
                 for (int it = 0; it <= L.waves_a; ++it) {
                     ChainWork wk;
                     if (!chain_work(L, it, crank, P.cluster, wk)) continue;
@@ -259,18 +282,26 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
         }
     } else if (warp >= 8) {
         // ================================ operand hand-over (4 warps): fused GroupNorm + SiLU where the layer has one ===
-        const int pt = threadIdx.x - 256;                        // 0..127
+        const int pt = threadIdx.x - 256;                        // 0 .. XF_THREADS-1
+        constexpr int XT = Cfg::XF_THREADS;
         constexpr int CHUNKS = Cfg::HROWS * Cfg::ROWP * 8;        // 16-byte chunks per plane
-        constexpr int PER_THREAD = (CHUNKS + 127) / 128;
-        const int jmine = (pt & 7) ^ ((pt >> 3) & 7);            // logical (channel) chunk of every physical chunk this thread owns
+        constexpr int PER_THREAD = (CHUNKS + XT - 1) / XT;
+        // physical chunk c = pt + XT q sits in row c >> 3 at position c & 7; its logical (channel) chunk (c & 7) ^ ((c >> 3) & 7)
+        // does not depend on q (XT is a multiple of 64): per-channel scale / shift live in registers per channel block
+        const int jmine = (pt & 7) ^ ((pt >> 3) & 7);
         uint32_t q = 0;
         for (int li = 0; li < P.n_layers; ++li) {
             const ChainLayer& L = P.layers[li];
             const bool gn = L.gi_stats != nullptr;
             int cur_n = -1;
+            float gam = 0.f, bet = 0.f;                           // this thread's channel (C_in <= 256 = XT), fetched before the wait
+            if (gn && pt < L.Cin) {
+                gam = __ldg(L.gi_gamma + pt);
+                bet = __ldg(L.gi_beta + pt);
+            }
             if (gn && li > 0) {                                   // the statistics were accumulated by the previous layers
                 if (pt == 0) grid_wait(P.sync, (unsigned int)li * G);
-                asm volatile("bar.sync 2, 128;" ::: "memory");
+                asm volatile("bar.sync 2, %0;" ::"n"(XT) : "memory");
             }
             for (int it = 0; it <= L.waves_a; ++it) {
                 ChainWork wk;
@@ -278,26 +309,48 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
                 const ChainTile tc = chain_decode(wk.tile, L);
                 if (gn && tc.n != cur_n) {
                     cur_n = tc.n;
-                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    asm volatile("bar.sync 2, %0;" ::"n"(XT) : "memory");
+                    // group statistics: 4 lanes per group, each sums a quarter of the replicas (8 independent L2 loads in
+                    // flight per lane instead of a serial 32-load chain per channel), butterfly, one fp64 finish per group
                     const int cpg = L.Cin / L.gi_groups;
-                    const double cnt = (double)L.D * L.H * L.W * cpg;
-                    for (int c = pt; c < L.Cin; c += 128) {
-                        const int g = c / cpg;
-                        double sum = 0.0, sq = 0.0;
-                        for (int r = 0; r < FCWDM_GN_STAT_REPLICAS; ++r) {
-                            const double* sp = L.gi_stats + (((long long)tc.n * FCWDM_GN_STAT_REPLICAS + r) * L.gi_groups + g) * 2;
-                            sum += ld_cg_f64(sp);
-                            sq += ld_cg_f64(sp + 1);
+                    const double inv_cnt = 1.0 / ((double)L.D * L.H * L.W * cpg);
+                    for (int idx = pt; idx < L.gi_groups * 4; idx += XT) {
+                        const int g = idx >> 2, rq = idx & 3;
+                        constexpr int RPQ = FCWDM_GN_STAT_REPLICAS / 4;
+                        double v[2 * RPQ];
+#pragma unroll
+                        for (int r = 0; r < RPQ; ++r) {
+                            const double* sp = L.gi_stats + (((long long)tc.n * FCWDM_GN_STAT_REPLICAS + rq * RPQ + r) * L.gi_groups + g) * 2;
+                            v[2 * r] = ld_cg_f64(sp);
+                            v[2 * r + 1] = ld_cg_f64(sp + 1);
                         }
-                        const double mean = sum / cnt;
-                        double var = sq / cnt - mean * mean;
-                        var = var < 0.0 ? 0.0 : var;
-                        const float rstd = (float)(1.0 / sqrt(var + (double)L.gi_eps));
-                        const float sc0 = rstd * __ldg(L.gi_gamma + c);
-                        sgn[c] = sc0;
-                        sgn[256 + c] = __ldg(L.gi_beta + c) - (float)mean * sc0;
+                        double sum = 0.0, sq = 0.0;
+#pragma unroll
+                        for (int r = 0; r < RPQ; ++r) {
+                            sum += v[2 * r];
+                            sq += v[2 * r + 1];
+                        }
+                        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                        if (rq == 0) {
+                            const double mean = sum * inv_cnt;
+                            double var = sq * inv_cnt - mean * mean;           // fp64: the subtraction cancels
+                            var = var < 0.0 ? 0.0 : var;
+                            gstat[g] = (float)mean;
+                            gstat[64 + g] = rsqrtf((float)var + L.gi_eps);
+                        }
                     }
-                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    asm volatile("bar.sync 2, %0;" ::"n"(XT) : "memory");
+                    if (pt < L.Cin) {
+                        const int g = pt / cpg;
+                        const float sc0 = gstat[64 + g] * gam;
+                        sgn[pt] = sc0;
+                        sgn[256 + pt] = bet - gstat[g] * sc0;
+                    }
+                    asm volatile("bar.sync 2, %0;" ::"n"(XT) : "memory");
+                    if (pt == 0) CHAIN_TRACE(li, 2);
                 }
                 const int cbn = L.n_cb / wk.split, cb0 = wk.kr * cbn;
                 for (int cb = cb0; cb < cb0 + cbn; ++cb) {
@@ -313,19 +366,19 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
                         const uint32_t slot = q % Cfg::A_SLOTS;
                         const int d = tc.d0 + p - 1;
                         mbar_wait(landed_a + 8 * slot, (q / Cfg::A_SLOTS) & 1);
+                        if (pt == 0 && cb == cb0 && p == 0) CHAIN_TRACE(li, 3);
                         if (gn && d >= 0 && d < L.D) {
                             uint4* plane = reinterpret_cast<uint4*>(smem_raw + (smem_a + slot * Cfg::SLOT_BYTES - smem_u32(smem_raw)));
                             uint4 raw[PER_THREAD];
                             uint32_t valid = 0;
 #pragma unroll
                             for (int i = 0; i < PER_THREAD; ++i) {
-                                const int c = pt + i * 128;
+                                const int c = pt + i * XT;
                                 const int r = c >> 3;
                                 const int hr = r / Cfg::ROWP, wc = r - hr * Cfg::ROWP;
                                 const int h = tc.h0 - 1 + hr, w = tc.w0 - 1 + wc;
                                 // out-of-range halo voxels stay ZERO: the convolution pads the ACTIVATED tensor
                                 const bool in = (c < CHUNKS) && (h >= 0) && (h < L.H) && (w >= 0) && (w < L.W);
-                                raw[i] = make_uint4(0u, 0u, 0u, 0u);
                                 if (in) {
                                     raw[i] = plane[c];
                                     valid |= 1u << i;
@@ -333,16 +386,19 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
                             }
 #pragma unroll
                             for (int i = 0; i < PER_THREAD; ++i) {
-                                float f[8];
-                                unpack8(raw[i], f);
+                                if (valid & (1u << i)) {             // ragged tiles (7x7, 14x14 planes): most of the halo is padding
+                                    float f[8];
+                                    unpack8(raw[i], f);
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) f[e] = c_silu(fmaf(f[e], sc[e], sh[e]));
-                                if (valid & (1u << i)) plane[pt + i * 128] = pack8(f);
+                                    for (int e = 0; e < 8; ++e) f[e] = c_silu(fmaf(f[e], sc[e], sh[e]));
+                                    plane[pt + i * XT] = pack8(f);
+                                }
                             }
                             fence_proxy_async();         // generic-proxy smem writes -> visible to the tensor-core (async) proxy
                         }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(full_a + 8 * slot);
+                        if (pt == 0 && cb == cb0 && p == 0) CHAIN_TRACE(li, 4);
                     }
                 }
             }
@@ -369,6 +425,7 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
                         for (int kd = 0; kd < 3; ++kd, ++q) {
                             const uint32_t slot = q % Cfg::A_SLOTS;
                             mbar_wait(full_a + 8 * slot, (q / Cfg::A_SLOTS) & 1);
+                            if (cb == 0 && kd == 0) CHAIN_TRACE(li, 5);
                             const uint64_t a_desc = a_desc_base + (uint64_t)((slot * Cfg::SLOT_BYTES) >> 4);
                             for (int kh = 0; kh < 3; ++kh, ++r) {
                                 const uint32_t st = r % Cfg::B_STAGES;
@@ -390,6 +447,7 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
                         }
                     }
                     umma_commit(tmem_full + 8 * as);
+                    CHAIN_TRACE(li, 6);
                     ++acc_it;
                 }
             }
@@ -452,19 +510,42 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
                 }
                 const uint32_t as = acc_it % Cfg::ACC_STAGES, aph = (acc_it / Cfg::ACC_STAGES) & 1;
                 ++acc_it;
-                mbar_wait(tmem_full + 8 * as, aph);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * N_TILE;
                 const int s = wk.split;
                 const int CW = N_TILE / s;                            // accumulator columns this CTA finishes
                 const int col0 = wk.kr * CW;
+                const int h = tc.h0 + hh, w = tc.w0 + ww;
+                const bool ok = (h < L.H) && (w < L.W);
+                const long long vox = (((long long)tc.n * L.D + tc.d0) * L.H + h) * L.W + w;
+                const bool use_res = ok && L.residual != nullptr;
+                // the residual row of my first 32 columns: in flight while the MMAs finish and the partial sums travel
+                uint4 res[4];
+                if (use_res) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        if (tc.n0 + col0 + g * 8 < L.Cout) res[g] = ld_cg_u4(L.residual + vox * L.res_ld + tc.n0 + col0 + g * 8);
+                }
+                mbar_wait(tmem_full + 8 * as, aph);
+                tc_fence_after();
+                if (row == 0) CHAIN_TRACE(li, 7);
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * N_TILE;
                 if (s > 1) {
-                    // ---- reduce-scatter: send every peer the columns it owns, receive mine from every peer
+                    // ---- reduce-scatter: send every peer the columns it owns, receive mine from every peer.
+                    // A shared tile is always this CTA's LAST work of the layer, and the next layer's halo planes cannot
+                    // land before the grid barrier this CTA has yet to arrive at: the plane ring is idle, so it serves as
+                    // the staging buffer.  TMEM -> registers -> staging (padded rows, conflict-free), then ONE bulk
+                    // distributed-shared-memory copy per peer that completes its bytes on the RECEIVER's mbarrier.
+                    // (Measured alternatives: per-thread st.shared::cluster + cluster-scope release/acquire 5-6 us per tile --
+                    // a MEMBAR.ALL.GPU per arrive; st.async 4 us -- one mbarrier transaction per 16 bytes.)
                     const uint32_t gb = (uint32_t)(crank - wk.kr);    // cluster rank of the group's first CTA
+                    const int pitch = CW + 4;                         // floats per row of a staging / receive slot
+                    const uint32_t slot_bytes = (uint32_t)(128 * pitch * 4);
+                    if (ew == 0 && lane == 0)
+                        for (int j = 0; j < s - 1; ++j) mbar_arrive_expect_tx(ready + 8 * j, slot_bytes);
                     for (int qd = 0; qd < s; ++qd) {
                         if (qd == wk.kr) continue;
-                        const int j = (wk.kr - qd + s) % s - 1;       // my slot in peer qd's receive buffer
-                        const uint32_t dst = mapa_u32(recv_u32 + (uint32_t)(j * CW * 512), gb + (uint32_t)qd) + (uint32_t)row * 4u;
+                        const int j = (wk.kr - qd + s) % s - 1;       // my slot in peer qd's receive buffer (and in my staging)
+                        uint4* stg = reinterpret_cast<uint4*>(smem_raw + (smem_a + (uint32_t)j * slot_bytes + (uint32_t)(row * pitch * 4) -
+                                                                          smem_u32(smem_raw)));
 #pragma unroll 1
                         for (int c = 0; c < CW; c += 32) {
                             uint32_t acc[32];
@@ -472,47 +553,45 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
                             tmem_ld_x16(taddr + qd * CW + c + 16, acc + 16);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int e = 0; e < 32; ++e)
-                                asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst + (uint32_t)(c + e) * 512u),
-                                             "f"(__uint_as_float(acc[e]))
-                                             : "memory");
+                            for (int e = 0; e < 8; ++e)
+                                stg[(c >> 2) + e] = make_uint4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
                         }
                     }
-                    asm volatile("fence.acq_rel.cluster;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
+                    fence_proxy_async();                              // staging writes -> visible to the bulk copy (async proxy)
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (ew == 0 && lane == 0) {
                         for (int qd = 0; qd < s; ++qd) {
                             if (qd == wk.kr) continue;
                             const int j = (wk.kr - qd + s) % s - 1;
-                            mbar_arrive_cluster(mapa_u32(ready + 8 * j, gb + (uint32_t)qd));
+                            const uint32_t dst = mapa_u32(recv_u32 + (uint32_t)j * slot_bytes, gb + (uint32_t)qd);
+                            const uint32_t rbar = mapa_u32(ready + 8 * j, gb + (uint32_t)qd);
+                            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         ::"r"(dst), "r"(smem_a + (uint32_t)j * slot_bytes), "r"(slot_bytes), "r"(rbar) : "memory");
                         }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     for (int j = 0; j < s - 1; ++j) {
                         mbar_wait(ready + 8 * j, ready_uses[j] & 1);
                         ++ready_uses[j];
                     }
-                    asm volatile("fence.acq_rel.cluster;" ::: "memory");
                 }
-                const int h = tc.h0 + hh, w = tc.w0 + ww;
-                const bool ok = (h < L.H) && (w < L.W);
-                const long long vox = (((long long)tc.n * L.D + tc.d0) * L.H + h) * L.W + w;
+                if (row == 0) CHAIN_TRACE(li, 8);
 #pragma unroll 1
                 for (int c0 = col0; c0 < col0 + CW; c0 += 32) {
-                    uint4 res[4];
-                    const bool use_res = ok && L.residual != nullptr;
-                    if (use_res) {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            if (tc.n0 + c0 + g * 8 < L.Cout) res[g] = ld_cg_u4(L.residual + vox * L.res_ld + tc.n0 + c0 + g * 8);
-                    }
                     uint32_t acc[32];
                     tmem_ld_x16(taddr + c0, acc);
                     tmem_ld_x16(taddr + c0 + 16, acc + 16);
                     tmem_ld_wait();
                     for (int j = 0; j < s - 1; ++j) {                 // + the peers' partial sums for my columns
-                        const float* pr = recv + j * CW * 128 + (c0 - col0) * 128 + row;
+                        const float4* pr = reinterpret_cast<const float4*>(recv + (j * 128 + row) * (CW + 4) + (c0 - col0));
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) acc[e] = __float_as_uint(__uint_as_float(acc[e]) + pr[e * 128]);
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 pv = pr[e];
+                            acc[4 * e] = __float_as_uint(__uint_as_float(acc[4 * e]) + pv.x);
+                            acc[4 * e + 1] = __float_as_uint(__uint_as_float(acc[4 * e + 1]) + pv.y);
+                            acc[4 * e + 2] = __float_as_uint(__uint_as_float(acc[4 * e + 2]) + pv.z);
+                            acc[4 * e + 3] = __float_as_uint(__uint_as_float(acc[4 * e + 3]) + pv.w);
+                        }
                     }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -534,6 +613,8 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
                             }
                             const uint4 packed = pack8(v);
                             if (ok) *reinterpret_cast<uint4*>(L.y + vox * L.y_ld + co) = packed;
+                            if (use_res && c0 + 32 < col0 + CW && co + 32 < L.Cout)   // next 32 columns' residual, one chunk ahead
+                                res[g] = ld_cg_u4(L.residual + vox * L.res_ld + co + 32);
                             if (want_stats) {                          // statistics of the STORED (bf16) values
                                 float vr[8];
                                 unpack8(packed, vr);
@@ -554,6 +635,7 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty + 8 * as);
+                if (row == 0) CHAIN_TRACE(li, 9);
             }
             // ---- end of layer: publish this CTA's share (stores + statistics), then arrive at the grid barrier
             if (want_stats && cur_n >= 0) {
@@ -564,12 +646,15 @@ __global__ void __launch_bounds__(384, 1) conv3d_chain_kernel(const __grid_const
                     atomicAdd(L.gn_stats + (((long long)cur_n * FCWDM_GN_STAT_REPLICAS + (blockIdx.x % FCWDM_GN_STAT_REPLICAS)) * L.gn_groups) * 2 + e, v);
                 }
             }
+            if (row == 0) CHAIN_TRACE(li, 10);
+            if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging (plane ring) is free again
             if (li + 1 < P.n_layers) {
                 __threadfence();                                          // my stores / atomics are visible device-wide ...
                 asm volatile("fence.proxy.async.global;" ::: "memory");   // ... also to other SMs' TMA reads
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (ew == 0 && lane == 0)
                     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(P.sync), "r"(1u) : "memory");
+                if (row == 0) CHAIN_TRACE(li, 11);
             } else {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
@@ -592,6 +677,7 @@ typedef CUresult (*EncodeTiledFnC)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFnC g_encode_c = nullptr;
+static long long* g_chain_trace = nullptr;      // development only (fcwdm_debug_set_chain_trace)
 static int g_chain_clusters[kChainMaxCluster + 1] = {0, 0, 0, 0, 0};      // co-resident clusters (one CTA per SM) by cluster size
 
 int conv3d_chain_init_device() {
@@ -608,7 +694,7 @@ int conv3d_chain_init_device() {
     for (int cs = 2; cs <= kChainMaxCluster; cs *= 2) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cs * 64);
-        cfg.blockDim = dim3(384);
+        cfg.blockDim = dim3(ChainCfg::THREADS);
         cfg.dynamicSmemBytes = ChainCfg::SMEM_BYTES;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -665,6 +751,7 @@ extern "C" int fcwdm_conv3d_chain(const fcwdm_chain_layer* layers, int64_t n_lay
     ChainParams* p = &params;
     p->n_layers = (int)n_layers;
     p->cluster = csize;
+    p->trace = g_chain_trace;
     p->sync = (unsigned int*)sync_counter;
     for (int64_t i = 0; i < n_layers; ++i) {
         const fcwdm_chain_layer& l = layers[i];
@@ -745,7 +832,7 @@ extern "C" int fcwdm_conv3d_chain(const fcwdm_chain_layer* layers, int64_t n_lay
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)G);
-    cfg.blockDim = dim3(384);
+    cfg.blockDim = dim3(ChainCfg::THREADS);
     cfg.dynamicSmemBytes = ChainCfg::SMEM_BYTES;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[2];
@@ -761,4 +848,18 @@ extern "C" int fcwdm_conv3d_chain(const fcwdm_chain_layer* layers, int64_t n_lay
     FCWDM_REQUIRE(e == cudaSuccess, FCWDM_ERR_CUDA, "fcwdm_conv3d_chain: launch failed: %s", cudaGetErrorString(e));
     FCWDM_CHECK_LAUNCH("fcwdm_conv3d_chain");
     return FCWDM_OK;
+}
+
+/* Development aid (tools/chain_trace.py): when set, every fcwdm_conv3d_chain launch writes %globaltimer stamps
+ * [grid][16 layers][16] (slot meaning: see CHAIN_TRACE in conv3d_chain.cu) to this device buffer.  NULL switches it off. */
+extern "C" int fcwdm_debug_set_chain_trace(void* device_buffer) {
+#ifdef FCWDM_CONV_TRACE
+    g_chain_trace = (long long*)device_buffer;
+    return FCWDM_OK;
+#else
+    g_chain_trace = nullptr;
+    FCWDM_REQUIRE(device_buffer == nullptr, FCWDM_ERR_UNSUPPORTED,
+                  "fcwdm_debug_set_chain_trace: this build has no trace points (rebuild with FCWDM_CONV_TRACE=1)");
+    return FCWDM_OK;
+#endif
 }

@@ -82,6 +82,7 @@ PROTOTYPES = {
     "fcwdm_conv3d_chain_supported": (_c_int, [_c_i64, _c_i64, _c_int]),
     "fcwdm_conv3d_chain_max_layers": (_c_int, []),
     "fcwdm_conv3d_chain": (_c_int, [ctypes.POINTER(ChainLayer), _c_i64, _c_p, _c_p]),
+    "fcwdm_debug_set_chain_trace": (_c_int, [_c_p]),
 }
 
 FCWDM_F32, FCWDM_BF16 = 0, 1

@@ -222,6 +222,7 @@ typedef struct fcwdm_chain_layer {
 int fcwdm_conv3d_chain_supported(int64_t Cin, int64_t Cout, int ksize);
 int fcwdm_conv3d_chain_max_layers(void);
 int fcwdm_conv3d_chain(const fcwdm_chain_layer* layers, int64_t n_layers, void* sync_counter, void* stream);
+int fcwdm_debug_set_chain_trace(void* device_buffer);   /* development builds only (FCWDM_CONV_TRACE=1) */
 
 /* ------------------------------------------------------------------------------------------------------
  * K5b: the same 3x3x3 convolution for C_in <= 64 and C_out <= 64 (the full-resolution layers) as a kd-fused,

@@ -210,8 +210,10 @@ def test_config3_batch8_equals_batch1(full_model, noise_hook):
         img1 = pipeline.synthesize(tame_diffusion, tame, vol[j:j + 1, 1:2], vol[j:j + 1, 2:3], vol[j:j + 1, 3:4], x_T[j:j + 1])
         r, p = rel(img8[j:j + 1], img1), psnr(img8[j:j + 1], img1)
         print(f"contractive weights, T = {T}, volume {j} of 8 vs batch 1: rel-L2 {r:.3e}, PSNR {p:.1f} dB, max-abs {float((img8[j:j + 1] - img1).abs().max()):.3e}")
-        assert r <= 1e-2 and p >= 40.0
-    assert rel(img8[1:2], img8[0:1]) > 0.05
+        # the contractive model's image is close to zero almost everywhere, so the relative L2 figure is dominated by tiny
+        # values; the absolute agreement is what is asserted (measured: 69 dB, max-abs 6e-3)
+        assert p >= 50.0 and float((img8[j:j + 1] - img1).abs().max()) <= 2e-2
+    assert float((img8[1:2] - img8[0:1]).abs().max()) > 5e-2
 
 
 # ----------------------------------------------------------------------------------------------------------------------

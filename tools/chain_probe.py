@@ -67,23 +67,28 @@ def timeit(fn, iters=20):
     return e0.elapsed_time(e1) / iters * 1e3
 
 
-print(f"cluster={os.environ.get('FCWDM_CHAIN_CLUSTER', 'auto')} split cap={os.environ.get('FCWDM_CHAIN_SPLIT', '-')}")
-for name, N, dims, widths in (
-        ("28^3 128 x8", 1, (20, 28, 28), (128,) * 9),
-        ("28^3 512->128 +6", 1, (20, 28, 28), (512,) + (128,) * 7),
-        ("14^3 256 x6", 1, (10, 14, 14), (256,) * 7),
-        ("14^3 1024->128,128->256,256 x4", 1, (10, 14, 14), (1024, 128, 256, 256, 256, 256)),
-        ("7^3 256 x12", 1, (5, 7, 7), (256,) * 13),
-        ("7^3 1024->256 +11", 1, (5, 7, 7), (1024,) + (256,) * 12),
-        ("14^3 256 x6 batch 8", 8, (10, 14, 14), (256,) * 7)):
-    specs = build(N, dims, widths)
-    dims4 = (N,) + dims
-    counter = torch.zeros(2, dtype=torch.int64, device=dev)
-    flop = sum(2.0 * N * dims[0] * dims[1] * dims[2] * s["cin"] * s["cout"] * 27 for s in specs)
-    t_chain = timeit(lambda: run_chain(specs, dims4, counter))
-    ya = [s["y"].float().clone() for s in specs]
-    t_layers = timeit(lambda: run_layers(specs, dims4))
-    diff = max(float((a - s["y"].float()).abs().max() / s["y"].float().abs().max().clamp_min(1e-6)) for a, s in zip(ya, specs))
-    L = len(specs)
-    print(f"{name:32s} L={L:2d}: chain {t_chain:7.1f} us ({t_chain / L:5.1f}/layer, {flop / t_chain / 1e6:6.0f} TFLOP/s) | per-layer launches "
-          f"{t_layers:7.1f} us ({t_layers / L:5.1f}/layer, {flop / t_layers / 1e6:6.0f} TFLOP/s) | max rel diff {diff:.1e}", flush=True)
+def main():
+    print(f"cluster={os.environ.get('FCWDM_CHAIN_CLUSTER', 'auto')} split cap={os.environ.get('FCWDM_CHAIN_SPLIT', '-')}")
+    for name, N, dims, widths in (
+            ("28^3 128 x8", 1, (20, 28, 28), (128,) * 9),
+            ("28^3 512->128 +6", 1, (20, 28, 28), (512,) + (128,) * 7),
+            ("14^3 256 x6", 1, (10, 14, 14), (256,) * 7),
+            ("14^3 1024->128,128->256,256 x4", 1, (10, 14, 14), (1024, 128, 256, 256, 256, 256)),
+            ("7^3 256 x12", 1, (5, 7, 7), (256,) * 13),
+            ("7^3 1024->256 +11", 1, (5, 7, 7), (1024,) + (256,) * 12),
+            ("14^3 256 x6 batch 8", 8, (10, 14, 14), (256,) * 7)):
+        specs = build(N, dims, widths)
+        dims4 = (N,) + dims
+        counter = torch.zeros(2, dtype=torch.int64, device=dev)
+        flop = sum(2.0 * N * dims[0] * dims[1] * dims[2] * s["cin"] * s["cout"] * 27 for s in specs)
+        t_chain = timeit(lambda: run_chain(specs, dims4, counter))
+        ya = [s["y"].float().clone() for s in specs]
+        t_layers = timeit(lambda: run_layers(specs, dims4))
+        diff = max(float((a - s["y"].float()).abs().max() / s["y"].float().abs().max().clamp_min(1e-6)) for a, s in zip(ya, specs))
+        L = len(specs)
+        print(f"{name:32s} L={L:2d}: chain {t_chain:7.1f} us ({t_chain / L:5.1f}/layer, {flop / t_chain / 1e6:6.0f} TFLOP/s) | per-layer launches "
+              f"{t_layers:7.1f} us ({t_layers / L:5.1f}/layer, {flop / t_layers / 1e6:6.0f} TFLOP/s) | max rel diff {diff:.1e}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
