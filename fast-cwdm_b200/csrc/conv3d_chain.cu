@@ -22,13 +22,14 @@
 // Tile = 16 x 8 voxels of one depth plane x 128 output channels (M = 128, N = 128); operand staging, UMMA descriptors
 // and the row-shifted halo addressing are those of conv3d.cu.
 #include <stdlib.h>
+#include <string.h>
 
 #include "conv3d_gn.cuh"
 #include "tc_ptx.cuh"
 
 namespace fcwdm {
 
-constexpr int kChainMaxLayers = 16;
+constexpr int kChainMaxLayers = 32;
 constexpr int kChainMaxCluster = 4;      // cluster size is chosen per launch (2 or 4): 4 shortens the serial MMA chain of the
                                          // smallest layers 4x, 2 keeps every SM usable (33 clusters of 4 = 132 of 148 SMs on B200)
 
@@ -56,6 +57,14 @@ struct ChainLayer {
     const float* gi_beta;
     int gi_groups;
     float gi_eps;
+    // auxiliary (non-conv) operations of the same launch, executed by the epilogue + transform warps of every CTA:
+    //   kind 1 = Haar DWT  x (N,D,H,W,Cin) -> y = LLL * lll_scale + chan_bias, aux = 7 high bands * hi_scale (or null)
+    //   kind 2 = Haar IDWT x = LLL (N,D/2,H/2,W/2,Cin) * lll_scale, aux = 7 high bands -> y (N,D,H,W,Cin) + chan_bias
+    // gn_stats (optional) receives the GroupNorm statistics of y in both cases
+    int kind;
+    __nv_bfloat16* aux;
+    long long aux_ld, aux_sb;
+    float lll_scale, hi_scale;
 };
 
 struct ChainParams {
@@ -170,6 +179,164 @@ __device__ __forceinline__ long long chain_now() {
 #define CHAIN_TRACE(li, slot) do { } while (0)
 #endif
 
+
+// ---------------------------------------------------------------------------------------------------
+// auxiliary operations (wavelet down / up-sampling between the convs of a run) -- HBM/L2-bound elementwise passes
+// ---------------------------------------------------------------------------------------------------
+constexpr int kAuxWorkers = 128 + ChainCfg::XF_THREADS;      // epilogue warps + transform warps of one CTA
+
+__device__ __forceinline__ float chain_scale(float v, float scale) {
+    return (scale == (1.0f / 3.0f)) ? (v / 3.0f) : (v * scale);      // LLL / 3. is a true division in the reference
+}
+
+// One Haar analysis (kind 1) or synthesis (kind 2) pass over sample n by the workers of the whole grid; wid = this
+// thread's worker index in its CTA.  st8[0..7] / st8[8..15] accumulate per-channel sum / sum of squares of the STORED
+// output values of this worker's fixed 8-channel chunk (the grid stride is a multiple of the chunks per voxel).
+__device__ __forceinline__ void chain_aux_pass(const ChainLayer& L, int n, int wid, float* st8) {
+    const int C8 = L.Cin >> 3;
+    const int D2 = L.D >> 1, H2 = L.H >> 1, W2 = L.W >> 1;
+    const long long items = (long long)D2 * H2 * W2 * C8;
+    const long long stride = (long long)gridDim.x * kAuxWorkers;
+    const bool want = L.gn_stats != nullptr;
+    for (long long idx = (long long)blockIdx.x * kAuxWorkers + wid; idx < items; idx += stride) {
+        const int cq = (int)(idx % C8);
+        long long t = idx / C8;
+        const int ww = (int)(t % W2); t /= W2;
+        const int hh = (int)(t % H2);
+        const int dd = (int)(t / H2);
+        const long long vox2 = (((long long)n * D2 + dd) * H2 + hh) * W2 + ww;
+        const long long vox0 = (((long long)n * L.D + 2 * dd) * L.H + 2 * hh) * L.W + 2 * ww;
+        float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (L.chan_bias != nullptr) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(L.chan_bias + (long long)n * L.cb_ld + cq * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(L.chan_bias + (long long)n * L.cb_ld + cq * 8 + 4));
+            bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w;
+            bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
+        }
+        if (L.kind == 1) {
+            const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(L.residual);    // aux ops carry their input in `residual`
+            const __nv_bfloat16* src = x + vox0 * L.res_ld + cq * 8;
+            float in[8][8];      // [brick position i*4+j*2+k][channel]
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        unpack8(ld_cg_u4(src + ((long long)(i * L.H + j) * L.W + k) * L.res_ld), in[i * 4 + j * 2 + k]);
+            float ob[8][8];      // [band][channel]
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float xin[8], b[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) xin[q] = in[q][c];
+                haar_analysis(xin, b);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) ob[q][c] = b[q];
+            }
+            {
+                float o[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) o[c] = chain_scale(ob[0][c], L.lll_scale) + bs[c];
+                const uint4 packed = pack8(o);
+                *reinterpret_cast<uint4*>(L.y + vox2 * L.y_ld + cq * 8) = packed;
+                if (want) {
+                    float vr[8];
+                    unpack8(packed, vr);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        st8[c] += vr[c];
+                        st8[8 + c] = fmaf(vr[c], vr[c], st8[8 + c]);
+                    }
+                }
+            }
+            if (L.aux != nullptr) {
+#pragma unroll
+                for (int b = 1; b < 8; ++b) {
+                    float o[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) o[c] = chain_scale(ob[b][c], L.hi_scale);
+                    *reinterpret_cast<uint4*>(L.aux + (long long)(b - 1) * L.aux_sb + vox2 * L.aux_ld + cq * 8) = pack8(o);
+                }
+            }
+        } else {
+            const __nv_bfloat16* lll = reinterpret_cast<const __nv_bfloat16*>(L.residual);
+            float bnd[8][8];     // [band][channel]
+            unpack8(ld_cg_u4(lll + vox2 * L.res_ld + cq * 8), bnd[0]);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) bnd[0][c] *= L.lll_scale;
+#pragma unroll
+            for (int b = 1; b < 8; ++b) unpack8(ld_cg_u4(L.aux + (long long)(b - 1) * L.aux_sb + vox2 * L.aux_ld + cq * 8), bnd[b]);
+            float out[8][8];     // [brick position][channel]
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float b[8], xo[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) b[q] = bnd[q][c];
+                haar_synthesis(b, xo);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) out[q][c] = xo[q] + bs[c];
+            }
+            __nv_bfloat16* dst = L.y + vox0 * L.y_ld + cq * 8;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const uint4 packed = pack8(out[i * 4 + j * 2 + k]);
+                        *reinterpret_cast<uint4*>(dst + ((long long)(i * L.H + j) * L.W + k) * L.y_ld) = packed;
+                        if (want) {
+                            float vr[8];
+                            unpack8(packed, vr);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                st8[c] += vr[c];
+                                st8[8 + c] = fmaf(vr[c], vr[c], st8[8 + c]);
+                            }
+                        }
+                    }
+        }
+    }
+}
+
+// All kAuxWorkers threads of the CTA: run the op sample by sample, reduce the statistics (lanes sharing a channel chunk
+// -> per-warp rows in shared memory -> one fp64 atomic per (group, component) and CTA), fence the stores, meet on barrier 3.
+__device__ __forceinline__ void chain_aux_op(const ChainLayer& L, int wid, float* scratch) {
+    const int lane = wid & 31, wrp = wid >> 5;                    // 12 worker warps
+    const int C8 = L.Cin >> 3;                                    // 8, 16 or 32 (checked on the host)
+    const bool want = L.gn_stats != nullptr;
+    for (int n = 0; n < L.N; ++n) {
+        float st8[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) st8[i] = 0.f;
+        chain_aux_pass(L, n, wid, st8);
+        if (want) {
+            for (int off = 16; off >= C8; off >>= 1)              // lanes l, l + C8, ... own the same channel chunk
+#pragma unroll
+                for (int i = 0; i < 16; ++i) st8[i] += __shfl_xor_sync(0xffffffffu, st8[i], off);
+            if (lane < C8) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    scratch[(wrp * 2 + 0) * 256 + lane * 8 + c] = st8[c];          // [warp][component][channel]
+                    scratch[(wrp * 2 + 1) * 256 + lane * 8 + c] = st8[8 + c];
+                }
+            }
+            asm volatile("bar.sync 3, %0;" ::"n"(kAuxWorkers) : "memory");
+            if (wid < 2 * L.gn_groups) {
+                const int g = wid >> 1, comp = wid & 1;
+                double v = 0.0;
+                for (int w = 0; w < kAuxWorkers / 32; ++w)
+                    for (int c = g * L.gn_cpg; c < (g + 1) * L.gn_cpg; ++c) v += (double)scratch[(w * 2 + comp) * 256 + c];
+                atomicAdd(L.gn_stats + (((long long)n * FCWDM_GN_STAT_REPLICAS + (blockIdx.x % FCWDM_GN_STAT_REPLICAS)) * L.gn_groups) * 2 + wid, v);
+            }
+            asm volatile("bar.sync 3, %0;" ::"n"(kAuxWorkers) : "memory");
+        }
+    }
+    __threadfence();                                              // this worker's stores / atomics are visible device-wide
+    asm volatile("bar.sync 3, %0;" ::"n"(kAuxWorkers) : "memory");
+}
+
 constexpr int kCWarpProdA = 4, kCWarpProdB = 5, kCWarpAlloc = 6, kCWarpMma = 7;
 
 __global__ void __launch_bounds__(ChainCfg::THREADS, 1) conv3d_chain_kernel(const __grid_constant__ ChainParams P) {
@@ -235,6 +402,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) conv3d_chain_kernel(cons
             uint32_t q = 0;
             for (int li = 0; li < P.n_layers; ++li) {
                 const ChainLayer& L = P.layers[li];
+                if (L.kind != 0) continue;                            // auxiliary op: no operands to stage
                 CHAIN_TRACE(li, 0);
                 if (li > 0) {
                     grid_wait(P.sync, (unsigned int)li * G);          // the previous layer's output is complete everywhere
@@ -264,6 +432,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) conv3d_chain_kernel(cons
             uint32_t r = 0;
             for (int li = 0; li < P.n_layers; ++li) {
                 const ChainLayer& L = P.layers[li];
+                if (L.kind != 0) continue;
                 for (int it = 0; it <= L.waves_a; ++it) {
                     ChainWork wk;
                     if (!chain_work(L, it, crank, P.cluster, wk)) continue;
@@ -292,6 +461,14 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) conv3d_chain_kernel(cons
         uint32_t q = 0;
         for (int li = 0; li < P.n_layers; ++li) {
             const ChainLayer& L = P.layers[li];
+            if (L.kind != 0) {                                    // auxiliary op: these 8 warps are workers 128..383
+                if (li > 0) {
+                    if (pt == 0) grid_wait(P.sync, (unsigned int)li * G);
+                    asm volatile("bar.sync 2, %0;" ::"n"(XT) : "memory");
+                }
+                chain_aux_op(L, 128 + pt, recv);
+                continue;
+            }
             const bool gn = L.gi_stats != nullptr;
             int cur_n = -1;
             float gam = 0.f, bet = 0.f;                           // this thread's channel (C_in <= 256 = XT), fetched before the wait
@@ -413,6 +590,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) conv3d_chain_kernel(cons
             uint32_t q = 0, r = 0, acc_it = 0;
             for (int li = 0; li < P.n_layers; ++li) {
                 const ChainLayer& L = P.layers[li];
+                if (L.kind != 0) continue;
                 for (int it = 0; it <= L.waves_a; ++it) {
                     ChainWork wk;
                     if (!chain_work(L, it, crank, P.cluster, wk)) continue;
@@ -469,6 +647,15 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) conv3d_chain_kernel(cons
                 // is complete (the counter is cumulative: early arrivals would be counted towards the previous layer)
                 if (ew == 0 && lane == 0) grid_wait(P.sync, (unsigned int)li * G);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            if (L.kind != 0) {                                    // auxiliary op: these 4 warps are workers 0..127
+                chain_aux_op(L, row, recv);
+                if (li + 1 < P.n_layers) {                        // every worker has fenced its stores (barrier 3)
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                    if (ew == 0 && lane == 0)
+                        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(P.sync), "r"(1u) : "memory");
+                }
+                continue;
             }
             if (want_stats) {
                 my_stat[lane] = 0.f;
@@ -740,6 +927,7 @@ extern "C" int fcwdm_conv3d_chain(const fcwdm_chain_layer* layers, int64_t n_lay
         const long long g4 = (long long)g_chain_clusters[4] * 4;
         for (int64_t i = 0; i < n_layers; ++i) {
             const fcwdm_chain_layer& l = layers[i];
+            if (l.kind != FCWDM_CHAIN_CONV) continue;
             const long long tiles = l.N * l.D * ((l.H + 15) / 16) * ((l.W + 7) / 8) * (l.Cout / 128);
             if (tiles > g4) csize = 2;
         }
@@ -756,6 +944,43 @@ extern "C" int fcwdm_conv3d_chain(const fcwdm_chain_layer* layers, int64_t n_lay
     for (int64_t i = 0; i < n_layers; ++i) {
         const fcwdm_chain_layer& l = layers[i];
         ChainLayer& L = p->layers[i];
+        L.kind = (int)l.kind;
+        if (l.kind != FCWDM_CHAIN_CONV) {
+            // ---- auxiliary op: Haar DWT / IDWT on channels-last bf16, same operand meaning as fcwdm_dwt3d_cl / fcwdm_idwt3d_cl
+            FCWDM_REQUIRE(l.kind == FCWDM_CHAIN_DWT || l.kind == FCWDM_CHAIN_IDWT, FCWDM_ERR_INVALID,
+                          "fcwdm_conv3d_chain: op %d: unknown kind %d", (int)i, (int)l.kind);
+            FCWDM_REQUIRE(l.x && l.y && (l.kind == FCWDM_CHAIN_DWT || l.aux), FCWDM_ERR_INVALID,
+                          "fcwdm_conv3d_chain: op %d: null pointer", (int)i);
+            FCWDM_REQUIRE(l.N > 0 && l.D > 0 && l.H > 0 && l.W > 0 && l.D % 2 == 0 && l.H % 2 == 0 && l.W % 2 == 0,
+                          FCWDM_ERR_INVALID, "fcwdm_conv3d_chain: op %d: D, H, W must be positive and even", (int)i);
+            FCWDM_REQUIRE(l.Cin == 64 || l.Cin == 128 || l.Cin == 256, FCWDM_ERR_UNSUPPORTED,
+                          "fcwdm_conv3d_chain: op %d: in-chain DWT / IDWT need 64, 128 or 256 channels", (int)i);
+            FCWDM_REQUIRE(l.x_ld >= l.Cin && l.x_ld % 8 == 0 && l.y_ld >= l.Cin && l.y_ld % 8 == 0 &&
+                              (l.aux == nullptr || (l.aux_ld >= l.Cin && l.aux_ld % 8 == 0 && l.aux_sb % 8 == 0)) && l.cb_ld % 4 == 0,
+                          FCWDM_ERR_INVALID, "fcwdm_conv3d_chain: op %d: bad leading dimension", (int)i);
+            FCWDM_REQUIRE(((uintptr_t)l.x % 16 == 0) && ((uintptr_t)l.y % 16 == 0) && ((uintptr_t)l.aux % 16 == 0) &&
+                              ((uintptr_t)l.chan_bias % 16 == 0),
+                          FCWDM_ERR_INVALID, "fcwdm_conv3d_chain: op %d: pointers must be 16-byte aligned", (int)i);
+            if (l.gn_stats != nullptr)
+                FCWDM_REQUIRE(l.gn_groups > 0 && l.gn_groups <= 32 && l.Cin % l.gn_groups == 0, FCWDM_ERR_UNSUPPORTED,
+                              "fcwdm_conv3d_chain: op %d: fused statistics need 1 <= groups <= 32 dividing C", (int)i);
+            memset(&L.map_a, 0, sizeof(L.map_a));
+            memset(&L.map_b, 0, sizeof(L.map_b));
+            L.N = (int)l.N; L.D = (int)l.D; L.H = (int)l.H; L.W = (int)l.W;
+            L.Cout = (int)l.Cin; L.Cin = (int)l.Cin;
+            L.n_cb = 0; L.n_nt = L.n_wt = L.n_ht = 1; L.num_tiles = 0; L.waves_a = 0; L.split_b = 1;
+            L.bias = nullptr; L.chan_bias = l.chan_bias; L.cb_ld = l.cb_ld;
+            L.residual = (const __nv_bfloat16*)l.x; L.res_ld = l.x_ld;           // aux ops carry their input here
+            L.y = (__nv_bfloat16*)l.y; L.y_ld = l.y_ld;
+            L.gn_stats = l.gn_stats;
+            L.gn_groups = l.gn_stats ? (int)l.gn_groups : 0;
+            L.gn_cpg = l.gn_stats ? (int)(l.Cin / l.gn_groups) : 0;
+            L.gi_stats = nullptr; L.gi_gamma = L.gi_beta = nullptr; L.gi_groups = 0; L.gi_eps = 0.f;
+            L.aux = (__nv_bfloat16*)l.aux; L.aux_ld = l.aux_ld; L.aux_sb = l.aux_sb;
+            L.lll_scale = l.lll_scale; L.hi_scale = l.hi_scale;
+            continue;
+        }
+        L.aux = nullptr; L.aux_ld = L.aux_sb = 0; L.lll_scale = L.hi_scale = 1.f;
         FCWDM_REQUIRE(l.x && l.wp && l.y, FCWDM_ERR_INVALID, "fcwdm_conv3d_chain: layer %d: null pointer", (int)i);
         FCWDM_REQUIRE(l.N > 0 && l.D > 0 && l.H > 0 && l.W > 0 && l.N < 32768 && l.D < 32768 && l.H < 32768 && l.W < 32768,
                       FCWDM_ERR_INVALID, "fcwdm_conv3d_chain: layer %d: bad dimension", (int)i);
@@ -851,7 +1076,7 @@ extern "C" int fcwdm_conv3d_chain(const fcwdm_chain_layer* layers, int64_t n_lay
 }
 
 /* Development aid (tools/chain_trace.py): when set, every fcwdm_conv3d_chain launch writes %globaltimer stamps
- * [grid][16 layers][16] (slot meaning: see CHAIN_TRACE in conv3d_chain.cu) to this device buffer.  NULL switches it off. */
+ * [grid][32 ops][16] (slot meaning: see CHAIN_TRACE in conv3d_chain.cu) to this device buffer.  NULL switches it off. */
 extern "C" int fcwdm_debug_set_chain_trace(void* device_buffer) {
 #ifdef FCWDM_CONV_TRACE
     g_chain_trace = (long long*)device_buffer;

@@ -183,12 +183,13 @@ class WavUNetEngine:
         ok_pair = pk.pair and self.fuse_stats_pair and cpg and cpg % 2 == 0
         # single-CTA kernel: break-even against the separate (HBM-roofline) statistics pass on large tensors, but on the
         # low-resolution layers the statistics pass is a latency-bound launch of its own -> fuse there
-        ok_single = (not pk.pair) and (self.fuse_stats or rows <= self.fuse_stats_rows) and \
+        chain = self._chainable(pk, rows, x, gn_in)
+        ok_single = (not pk.pair) and (self.fuse_stats or rows <= self.fuse_stats_rows or chain) and \
             (cpg in (1, 2, 4) or (cpg and cpg % 8 == 0))
         if stats_groups and stats_groups <= 32 and (ok_pair or ok_single):
             stats = self._stats_slot(N, stats_groups, x.device)
             self._stats[id(y)] = (stats, stats_groups, y)     # holding y keeps its id unique until consumed
-        if self._chainable(pk, rows, x, gn_in):
+        if chain:
             # deferred: becomes one layer of the next fcwdm_conv3d_chain launch (flushed before any other kernel runs)
             self._chain.append(ops.conv3d_chain_layer(x, pk.wp, pk.bias, y, (N,) + tuple(dims), pk.cin, pk.cout,
                                                       chan_bias=chan_bias, residual=residual, gn_stats=stats,
@@ -211,6 +212,18 @@ class WavUNetEngine:
         if not ops.conv3d_chain_supported(pk.cin, pk.cout, 3) or x.stride(0) < pk.cin:
             return False
         return gn_in is None or pk.cin <= 256
+
+    def _aux_ok(self, rows, *channels):
+        """A wavelet re-sampling op can ride in the pending chain launch: low-resolution tensor, supported widths."""
+        return self.use_chain and rows <= self.chain_rows and all(ops.chain_aux_supported(c) for c in channels)
+
+    def _aux_stats(self, y, N, gn):
+        """Statistics slot for the output y of an in-chain DWT / IDWT whose consumer is GroupNorm `gn`."""
+        if gn is None or gn.num_groups > 32 or gn.num_channels % gn.num_groups:
+            return None, 0
+        stats = self._stats_slot(N, gn.num_groups, y.device)
+        self._stats[id(y)] = (stats, gn.num_groups, y)
+        return stats, gn.num_groups
 
     def _flush_chain(self):
         """Launch the deferred run of low-resolution convs (if any) as persistent chain launches."""
@@ -290,28 +303,41 @@ class WavUNetEngine:
         skip_out = skip
         if blk.down:
             h_full = self._gn_silu_conv(gn1, x, conv1, N, dims)
-            self._flush_chain()
             d2 = (dims[0] // 2, dims[1] // 2, dims[2] // 2)
             s2 = d2[0] * d2[1] * d2[2]
             h = self._buf(N * s2, cout, dev)
             hi = torch.empty((7, N * s2, _ld(cout)), dtype=torch.bfloat16, device=dev) if _ld(cout) == cout else \
                 torch.zeros((7, N * s2, _ld(cout)), dtype=torch.bfloat16, device=dev)
-            # h, hSkip = Downsample(h): LLL/3 (+ emb, :262) and the 7 high bands (:118-121, :240)
-            ops.dwt3d_cl(h_full, (N,) + tuple(dims), cout, h, hi, lll_bias=emb_add, lll_scale=1.0 / 3.0)
             xs = self._buf(N * s2, cin, dev)
-            ops.dwt3d_cl(x, (N,) + tuple(dims), cin, xs, None, lll_scale=1.0 / 3.0)      # x_upd: LLL/3 only (:241)
+            # h, hSkip = Downsample(h): LLL/3 (+ emb, :262) and the 7 high bands (:118-121, :240); x_upd: LLL/3 only (:241)
+            if self._aux_ok(N * S, cout, cin):
+                st, g = self._aux_stats(h, N, None if ssn else blk.out_layers[0])
+                self._chain.append(ops.chain_dwt_op(h_full, (N,) + tuple(dims), cout, h, hi, lll_bias=emb_add,
+                                                    lll_scale=1.0 / 3.0, gn_stats=st, gn_groups=g))
+                self._chain.append(ops.chain_dwt_op(x, (N,) + tuple(dims), cin, xs, None, lll_scale=1.0 / 3.0))
+            else:
+                self._flush_chain()
+                ops.dwt3d_cl(h_full, (N,) + tuple(dims), cout, h, hi, lll_bias=emb_add, lll_scale=1.0 / 3.0)
+                ops.dwt3d_cl(x, (N,) + tuple(dims), cin, xs, None, lll_scale=1.0 / 3.0)
             x, dims, S, skip_out = xs, d2, s2, hi
         elif blk.up:
             if skip is None:
                 raise FcwdmError("up-sampling ResBlock reached without stored high-frequency sub-bands")
             h_low = self._gn_silu_conv(gn1, x, conv1, N, dims)
-            self._flush_chain()
             d2 = (dims[0] * 2, dims[1] * 2, dims[2] * 2)
             s2 = d2[0] * d2[1] * d2[2]
             h = self._buf(N * s2, cout, dev)
-            ops.idwt3d_cl(h_low, skip, (N,) + d2, cout, h, bias=emb_add, lll_scale=3.0)   # IDWT(3h, skip) + emb
             xu = self._buf(N * s2, cin, dev)
-            ops.idwt3d_cl(x, skip, (N,) + d2, cin, xu, bias=None, lll_scale=3.0)          # IDWT(3x, skip)
+            # h = IDWT(3h, skip) + emb; x = IDWT(3x, skip)
+            if self._aux_ok(N * s2, cout, cin) and skip.stride(-2) >= max(cin, cout):
+                st, g = self._aux_stats(h, N, None if ssn else blk.out_layers[0])
+                self._chain.append(ops.chain_idwt_op(h_low, skip, (N,) + d2, cout, h, bias=emb_add, lll_scale=3.0,
+                                                     gn_stats=st, gn_groups=g))
+                self._chain.append(ops.chain_idwt_op(x, skip, (N,) + d2, cin, xu, bias=None, lll_scale=3.0))
+            else:
+                self._flush_chain()
+                ops.idwt3d_cl(h_low, skip, (N,) + d2, cout, h, bias=emb_add, lll_scale=3.0)
+                ops.idwt3d_cl(x, skip, (N,) + d2, cin, xu, bias=None, lll_scale=3.0)
             x, dims, S, skip_out = xu, d2, s2, None
         else:
             h = self._gn_silu_conv(gn1, x, conv1, N, dims, chan_bias=emb_add,             # conv + emb (:262)
@@ -385,9 +411,13 @@ class WavUNetEngine:
                 d2 = (pyr_dims[0] // 2, pyr_dims[1] // 2, pyr_dims[2] // 2)
                 s2 = d2[0] * d2[1] * d2[2]
                 cat = self._buf(N * s2, 8 * pyr_c, x_cl.device)
-                self._flush_chain()
-                ops.dwt3d_cl(pyramid, (N,) + pyr_dims, pyr_c, cat[:, :pyr_c], cat[:, pyr_c:], lll_scale=1.0 / 3.0,
-                             hi_scale=1.0 / 3.0, hi_sb=pyr_c)
+                if self._aux_ok(N * pyr_dims[0] * pyr_dims[1] * pyr_dims[2], pyr_c):
+                    self._chain.append(ops.chain_dwt_op(pyramid, (N,) + pyr_dims, pyr_c, cat[:, :pyr_c], cat[:, pyr_c:],
+                                                        lll_scale=1.0 / 3.0, hi_scale=1.0 / 3.0, hi_sb=pyr_c))
+                else:
+                    self._flush_chain()
+                    ops.dwt3d_cl(pyramid, (N,) + pyr_dims, pyr_c, cat[:, :pyr_c], cat[:, pyr_c:], lll_scale=1.0 / 3.0,
+                                 hi_scale=1.0 / 3.0, hi_sb=pyr_c)
                 pyramid = self._conv3d(first.conv, cat, N, d2, residual=h, stats_groups=m.num_groups)
                 pyr_dims, pyr_c = d2, first.out_ch
                 h = pyramid

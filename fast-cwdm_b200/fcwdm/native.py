@@ -22,7 +22,8 @@ class ChainLayer(ctypes.Structure):
                 ("residual", _c_p), ("res_ld", _c_i64), ("y", _c_p), ("y_ld", _c_i64), ("gn_stats", _c_p),
                 ("gn_groups", _c_i64), ("gn_in_stats", _c_p), ("gn_in_gamma", _c_p), ("gn_in_beta", _c_p),
                 ("gn_in_groups", _c_i64), ("gn_in_eps", _c_f), ("N", _c_i64), ("D", _c_i64), ("H", _c_i64), ("W", _c_i64),
-                ("Cin", _c_i64), ("Cout", _c_i64)]
+                ("Cin", _c_i64), ("Cout", _c_i64), ("kind", _c_i64), ("aux", _c_p), ("aux_ld", _c_i64), ("aux_sb", _c_i64),
+                ("lll_scale", _c_f), ("hi_scale", _c_f)]
 
 
 # name -> (restype, argtypes); mirrors include/fcwdm.h one to one

@@ -282,6 +282,47 @@ def conv3d_chain_layer(x, wp, bias, y, dims, cin, cout, chan_bias=None, residual
     return L, (x, wp, bias, y, chan_bias, residual, gn_stats, gn_in)
 
 
+CHAIN_CONV, CHAIN_DWT, CHAIN_IDWT = 0, 1, 2
+
+
+def chain_aux_supported(C):
+    return C in (64, 128, 256)
+
+
+def chain_dwt_op(x, dims, C, lll, hi, lll_bias=None, lll_scale=1.0 / 3.0, hi_scale=1.0, hi_sb=None, gn_stats=None, gn_groups=0):
+    """dwt3d_cl as an op of a conv3d_chain launch (same arguments); gn_stats: statistics of the LLL output."""
+    N, D, H, W = dims
+    L = native.ChainLayer()
+    L.kind = CHAIN_DWT
+    L.x, L.x_ld, L.y, L.y_ld = x.data_ptr(), x.stride(0), lll.data_ptr(), lll.stride(0)
+    if hi is not None:
+        L.aux, L.aux_ld = hi.data_ptr(), hi.stride(-2)
+        L.aux_sb = hi_sb if hi_sb is not None else hi.stride(0)
+    if lll_bias is not None:
+        L.chan_bias, L.cb_ld = lll_bias.data_ptr(), lll_bias.stride(0)
+    L.lll_scale, L.hi_scale = float(lll_scale), float(hi_scale)
+    if gn_stats is not None:
+        L.gn_stats, L.gn_groups = gn_stats.data_ptr(), gn_groups
+    L.N, L.D, L.H, L.W, L.Cin, L.Cout = N, D, H, W, C, C
+    return L, (x, lll, hi, lll_bias, gn_stats)
+
+
+def chain_idwt_op(lll, hi, dims_out, C, y, bias=None, lll_scale=3.0, gn_stats=None, gn_groups=0):
+    """idwt3d_cl as an op of a conv3d_chain launch (same arguments); gn_stats: statistics of the output y."""
+    N, D, H, W = dims_out
+    L = native.ChainLayer()
+    L.kind = CHAIN_IDWT
+    L.x, L.x_ld, L.y, L.y_ld = lll.data_ptr(), lll.stride(0), y.data_ptr(), y.stride(0)
+    L.aux, L.aux_ld, L.aux_sb = hi.data_ptr(), hi.stride(-2), hi.stride(0)
+    if bias is not None:
+        L.chan_bias, L.cb_ld = bias.data_ptr(), bias.stride(0)
+    L.lll_scale, L.hi_scale = float(lll_scale), 1.0
+    if gn_stats is not None:
+        L.gn_stats, L.gn_groups = gn_stats.data_ptr(), gn_groups
+    L.N, L.D, L.H, L.W, L.Cin, L.Cout = N, D, H, W, C, C
+    return L, (lll, hi, y, bias, gn_stats)
+
+
 def conv3d_chain(layers, sync_counter):
     """Run a list of conv3d_chain_layer structs as ONE persistent launch (csrc/conv3d_chain.cu).  sync_counter: a device
     tensor whose first 4 bytes are zero (the grid-barrier counter)."""

@@ -30,6 +30,7 @@ class ScheduleSampler:
         w = np.asarray(self.weights(), dtype=np.float64)
         p = w / w.sum()
         picked = np.random.choice(len(p), size=(batch_size,), p=p)
+        self.last_indices = picked                      # host copy of the draw (logging keys that depend on t need no read-back)
         scale = 1.0 / (len(p) * p[picked])
         t_host = th.from_numpy(picked).long()
         w_host = th.from_numpy(scale).float()

@@ -321,6 +321,14 @@ class TrainLoop:
         for i, name in enumerate(BAND_NAMES):
             logger.logkv_mean(f"mse_wav_{name.lower()}", mse_wav[i].detach())
         logger.logkv_mean("loss", lossmse)
+        # the reference's log_loss_dict columns (train_util.py:554-560): the band mean under "mse_wav", and -- it zips the B
+        # timesteps with the 8 band values -- band i under the quartile of t[i]; the timesteps come from the sampler's host
+        # copy of its draw, the values stay on the device until the logger dumps
+        logger.logkv_mean("mse_wav", lossmse)
+        t_host = getattr(self.schedule_sampler, "last_indices", None)
+        if t_host is not None:
+            for i, ti in enumerate(t_host[:len(BAND_NAMES)]):
+                logger.logkv_mean(f"mse_wav_q{int(4 * int(ti) / self.diffusion.num_timesteps)}", mse_wav[i].detach())
         loss.backward()
         return lossmse, sample, sample_idwt
 

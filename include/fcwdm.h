@@ -218,7 +218,20 @@ typedef struct fcwdm_chain_layer {
     int64_t gn_in_groups;
     float gn_in_eps;
     int64_t N, D, H, W, Cin, Cout;
+    /* kind != FCWDM_CHAIN_CONV: a wavelet re-sampling op between the convs of the run, executed by the same launch
+     * (same operand meaning as fcwdm_dwt3d_cl / fcwdm_idwt3d_cl; wp, bias, residual, gn_in_* and Cout are ignored):
+     *   FCWDM_CHAIN_DWT : x (N,D,H,W,Cin) -> y = LLL * lll_scale + chan_bias[n], aux = the 7 high bands * hi_scale (or NULL)
+     *   FCWDM_CHAIN_IDWT: x = LLL (N,D/2,H/2,W/2,Cin) * lll_scale, aux = the 7 high bands -> y (N,D,H,W,Cin) + chan_bias[n]
+     * band b of aux starts at aux + b * aux_sb (elements), voxel stride aux_ld; gn_stats (optional, pre-zeroed) receives
+     * the GroupNorm statistics of y.  Cin must be 64, 128 or 256. */
+    int64_t kind;
+    void* aux;
+    int64_t aux_ld, aux_sb;
+    float lll_scale, hi_scale;
 } fcwdm_chain_layer;
+#define FCWDM_CHAIN_CONV 0
+#define FCWDM_CHAIN_DWT 1
+#define FCWDM_CHAIN_IDWT 2
 int fcwdm_conv3d_chain_supported(int64_t Cin, int64_t Cout, int ksize);
 int fcwdm_conv3d_chain_max_layers(void);
 int fcwdm_conv3d_chain(const fcwdm_chain_layer* layers, int64_t n_layers, void* sync_counter, void* stream);

@@ -195,3 +195,83 @@ def test_engine_uses_the_chain_and_matches_the_per_layer_plan(monkeypatch):
     print(f"chain {r_chain:.3e} vs per-layer {r_plain:.3e} rel-L2 against the oracle; launches {launches['0']} vs {launches['1']}")
     assert r_chain <= 3e-2 and r_plain <= 3e-2
     assert launches["0"] < launches["1"]
+
+
+@pytest.mark.parametrize("C,dims,N", [(128, (20, 28, 28), 1), (256, (10, 14, 14), 1), (64, (4, 6, 10), 2), (128, (2, 14, 14), 3)])
+def test_chain_wavelet_ops_equal_the_standalone_kernels(C, dims, N):
+    """In-chain Haar DWT / IDWT (the ResBlock re-sampling between the convs of a run) == fcwdm_dwt3d_cl / fcwdm_idwt3d_cl
+    bit for bit (same butterfly, same scaling), and their fused GroupNorm statistics == the statistics of what they stored."""
+    from fcwdm import ops
+    D, H, W = dims
+    S, s2 = D * H * W, (D // 2) * (H // 2) * (W // 2)
+    gen = torch.Generator().manual_seed(C + D)
+    x = torch.randn(N * S, C, generator=gen).cuda().to(torch.bfloat16)
+    emb = torch.randn(N, C, generator=gen).cuda()
+    # --- reference: the standalone kernels
+    lll_ref = torch.zeros((N * s2, C), dtype=torch.bfloat16, device="cuda")
+    hi_ref = torch.zeros((7, N * s2, C), dtype=torch.bfloat16, device="cuda")
+    ops.dwt3d_cl(x, (N, D, H, W), C, lll_ref, hi_ref, lll_bias=emb, lll_scale=1.0 / 3.0)
+    only_ref = torch.zeros((N * s2, C), dtype=torch.bfloat16, device="cuda")
+    ops.dwt3d_cl(x, (N, D, H, W), C, only_ref, None, lll_scale=1.0 / 3.0)
+    cat_ref = torch.zeros((N * s2, 8 * C), dtype=torch.bfloat16, device="cuda")
+    ops.dwt3d_cl(x, (N, D, H, W), C, cat_ref[:, :C], cat_ref[:, C:], lll_scale=1.0 / 3.0, hi_scale=1.0 / 3.0, hi_sb=C)
+    y_ref = torch.zeros((N * S, C), dtype=torch.bfloat16, device="cuda")
+    ops.idwt3d_cl(lll_ref, hi_ref, (N, D, H, W), C, y_ref, bias=emb, lll_scale=3.0)
+    # --- the same four ops as ONE chain launch (the IDWT consumes what the first DWT of the same launch produced)
+    lll = torch.zeros_like(lll_ref)
+    hi = torch.zeros_like(hi_ref)
+    only = torch.zeros_like(only_ref)
+    cat = torch.zeros_like(cat_ref)
+    y = torch.zeros_like(y_ref)
+    st_l = torch.zeros((N, ops.GN_STAT_REPLICAS, G, 2), dtype=torch.float64, device="cuda")
+    st_y = torch.zeros_like(st_l)
+    layers = [ops.chain_dwt_op(x, (N, D, H, W), C, lll, hi, lll_bias=emb, lll_scale=1.0 / 3.0, gn_stats=st_l, gn_groups=G),
+              ops.chain_dwt_op(x, (N, D, H, W), C, only, None, lll_scale=1.0 / 3.0),
+              ops.chain_dwt_op(x, (N, D, H, W), C, cat[:, :C], cat[:, C:], lll_scale=1.0 / 3.0, hi_scale=1.0 / 3.0, hi_sb=C),
+              ops.chain_idwt_op(lll, hi, (N, D, H, W), C, y, bias=emb, lll_scale=3.0, gn_stats=st_y, gn_groups=G)]
+    ops.conv3d_chain([l for l, _ in layers], torch.zeros(2, dtype=torch.int64, device="cuda"))
+    torch.cuda.synchronize()
+    for name, a, b in (("lll", lll, lll_ref), ("hi", hi, hi_ref), ("lll only", only, only_ref), ("concat", cat, cat_ref), ("idwt", y, y_ref)):
+        assert torch.equal(a, b), name
+    for st, t, rows in ((st_l, lll, s2), (st_y, y, S)):
+        v = t.double().reshape(N, rows, G, C // G)
+        s = st.sum(dim=1)
+        np.testing.assert_allclose(s[..., 0].cpu().numpy(), v.sum(dim=(1, 3)).cpu().numpy(), rtol=1e-5, atol=1e-3)
+        np.testing.assert_allclose(s[..., 1].cpu().numpy(), (v * v).sum(dim=(1, 3)).cpu().numpy(), rtol=1e-5, atol=1e-3)
+
+
+def test_chain_conv_dwt_conv():
+    """conv -> in-chain DWT (LLL / 3 + embedding, fused statistics) -> conv with fused input GroupNorm from those
+    statistics, in one launch, against torch fp32 step by step."""
+    from fcwdm import ops
+    from gpu_util import bf16_round, from_cl, to_cl
+    N, (D, H, W), C = 1, (10, 14, 14), 128
+    S, s2 = D * H * W, (D // 2) * (H // 2) * (W // 2)
+    gen = torch.Generator().manual_seed(11)
+    x0 = _mk(gen, N, C, D, H, W)
+    w1, w2 = (_mk(gen, C, C, 3, 3, 3, scale=1.0 / np.sqrt(C * 27)) for _ in range(2))
+    b1, b2 = torch.randn(C, generator=gen).cuda(), torch.randn(C, generator=gen).cuda()
+    emb = torch.randn(N, C, generator=gen).cuda()
+    gamma, beta = (torch.rand(C, generator=gen) + 0.5).cuda(), (torch.randn(C, generator=gen) * 0.2).cuda()
+    xc = to_cl(x0)
+    y1 = torch.zeros((N * S, C), dtype=torch.bfloat16, device="cuda")
+    lll = torch.zeros((N * s2, C), dtype=torch.bfloat16, device="cuda")
+    hi = torch.zeros((7, N * s2, C), dtype=torch.bfloat16, device="cuda")
+    y2 = torch.zeros((N * s2, C), dtype=torch.bfloat16, device="cuda")
+    st = torch.zeros((N, ops.GN_STAT_REPLICAS, G, 2), dtype=torch.float64, device="cuda")
+    layers = [ops.conv3d_chain_layer(xc, ops.conv3d_pack_weights(w1), b1, y1, (N, D, H, W), C, C),
+              ops.chain_dwt_op(y1, (N, D, H, W), C, lll, hi, lll_bias=emb, lll_scale=1.0 / 3.0, gn_stats=st, gn_groups=G),
+              ops.conv3d_chain_layer(lll, ops.conv3d_pack_weights(w2), b2, y2, (N, D // 2, H // 2, W // 2), C, C,
+                                     gn_in=(st, gamma, beta, G, EPS))]
+    ops.conv3d_chain([l for l, _ in layers], torch.zeros(2, dtype=torch.int64, device="cuda"))
+    torch.cuda.synchronize()
+    got1 = from_cl(y1, (N, C, D, H, W))
+    ref1 = _ref_layer(x0, w1, b1, None, None, None)
+    assert float((got1 - ref1).abs().max()) <= 1e-2 * float(ref1.abs().max()) + 1e-3
+    lll_ref = torch.zeros_like(lll)
+    ops.dwt3d_cl(y1, (N, D, H, W), C, lll_ref, torch.zeros_like(hi), lll_bias=emb, lll_scale=1.0 / 3.0)
+    assert torch.equal(lll, lll_ref)
+    xin = from_cl(lll, (N, C, D // 2, H // 2, W // 2))
+    ref2 = _ref_layer(xin, w2, b2, None, None, (gamma, beta))
+    got2 = from_cl(y2, (N, C, D // 2, H // 2, W // 2))
+    assert float((got2 - ref2).abs().max()) <= 1e-2 * float(ref2.abs().max()) + 1e-3

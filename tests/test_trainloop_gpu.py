@@ -3,6 +3,8 @@ configuration through the public surface scripts/train.py uses -- create_named_s
 -- compared with the same steps written out by hand (training_losses + backward + FusedAdamW, what
 tests/test_train_gpu.py pins to the reference fixture), plus the checkpoint / resume cycle."""
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -147,6 +149,74 @@ def test_trainloop_matches_hand_written_steps_and_checkpoints(tmp_path, monkeypa
         assert torch.equal(loop4.opt.m, loop3.opt.m) and torch.equal(loop4.opt.v, loop3.opt.v)
         for (n3, p3), (n4, p4) in zip(m3.named_parameters(), m4.named_parameters()):
             assert torch.equal(p3, p4), n3
+    finally:
+        logger.reset()
+
+
+def test_trainloop_matches_three_steps_of_the_unmodified_reference(tmp_path, monkeypatch, golden):
+    """tests/golden/trainloop_steps.npz = three real steps of the reference's own TrainLoop on the CPU in fp32
+    (oracle/make_golden_trainloop_steps.py): same model, data, timesteps (np.random.seed(0)) and -- replayed from the
+    fixture -- the same image-space noise.  The drop-in's loss trajectory, logger columns, checkpoint files, best-loss
+    table, optimizer step count, annealed learning rate and stepped parameters must agree (bf16 compute tolerance)."""
+    from unittest import mock
+    from guided_diffusion import logger
+    from guided_diffusion.script_util import create_gaussian_diffusion
+    g = golden("trainloop_steps")
+    monkeypatch.setenv("FCWDM_CHECKPOINT_ROOT", str(tmp_path))
+    logger.configure(dir=str(tmp_path / "log"), format_strs=["csv"])
+    try:
+        d10 = create_gaussian_diffusion(steps=10, predict_xstart=True, sample_schedule="sampled", mode="i2i")
+        np.random.seed(0)
+        torch.manual_seed(0)
+        model = fresh_model()
+        start = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        loop = make_loop(model, d10, 4)
+        drawn = []
+        orig = loop.schedule_sampler.sample
+
+        def sample(batch_size, device):
+            t, w = orig(batch_size, device)
+            drawn.append(t.cpu().numpy())
+            return t, w
+
+        loop.schedule_sampler.sample = sample
+        noises = iter(torch.from_numpy(g["noise"]))
+        with mock.patch.object(torch, "randn_like", side_effect=lambda x, *a, **k: next(noises).to(x.device)):
+            loop.run_loop()
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(np.stack(drawn), g["t"])                      # same UniformSampler draws
+        rows = list(__import__("csv").DictReader(open(tmp_path / "log" / "progress.csv")))
+        got = np.array([float(r["loss"]) for r in rows])
+        print("TrainLoop loss", got, "reference", g["loss"])
+        np.testing.assert_allclose(got, g["loss"], rtol=1e-2)                       # stated: loss within 1e-2 relative
+        assert [int(float(r["step"])) for r in rows] == list(g["step"])
+        assert [int(float(r["samples"])) for r in rows] == list(g["samples"])
+        assert set(g["csv_columns"]) <= set(rows[0].keys())                          # every column the reference logs
+        np.testing.assert_allclose([float(r["mse_wav"]) for r in rows], g["loss"], rtol=1e-2)
+        files = sorted(os.listdir(tmp_path / "checkpoints"))
+        assert files == list(g["checkpoint_files"])                                  # same files under checkpoints/
+        ref_best = float(str(g["best_losses_txt"]).strip().split(":")[1])
+        table = dict(l.strip().split(":") for l in open(tmp_path / "checkpoints" / "best_losses.txt"))
+        assert set(table) == {"t1n"} and float(table["t1n"]) == pytest.approx(ref_best, rel=1e-2)
+        opt_sd = torch.load(tmp_path / "checkpoints" / "opt_best_t1n.pt", map_location="cpu")
+        assert sorted(opt_sd.keys()) == list(g["opt_state_keys"])
+        assert loop.opt.step_count == int(g["opt_step"])
+        assert loop.opt.param_groups[0]["lr"] == pytest.approx(float(g["final_lr"]), rel=1e-9)
+        # parameters after three AdamW steps: the UPDATE (final - start) against the reference's update
+        final = model.state_dict()
+        for k in ("out.2.bias", "time_embed.0.bias", "input_blocks.0.0.bias", "middle_block.0.in_layers.0.weight"):
+            got_d = (final[k] - start[k]).float().cpu().numpy()
+            ref_d = g["delta/" + k]
+            err = np.linalg.norm(got_d - ref_d) / max(np.linalg.norm(ref_d), 1e-12)
+            print(f"update of {k}: rel-L2 {err:.3e}")
+            assert err <= 0.15, (k, err)                                              # Adam normalises: sign flips of tiny gradients dominate
+        names = list(g["param_names"])
+        num = den = 0.0
+        for k, ref_n in zip(names, g["param_delta_norms"]):
+            d = float((final[k] - start[k]).double().norm())
+            num += (d - ref_n) ** 2
+            den += ref_n ** 2
+        assert (num / den) ** 0.5 <= 5e-2                                            # size of every tensor's update
     finally:
         logger.reset()
 

@@ -21,7 +21,7 @@ for name, N, dims, widths in (("7^3 256 x6", 1, (5, 7, 7), (256,) * 7), ("14^3 2
     specs = cp.build(N, dims, widths)
     dims4 = (N,) + dims
     counter = torch.zeros(2, dtype=torch.int64, device=dev)
-    trace = torch.zeros((160, 16, 16), dtype=torch.int64, device=dev)
+    trace = torch.zeros((160, 32, 16), dtype=torch.int64, device=dev)
     for _ in range(3):
         cp.run_chain(specs, dims4, counter)
     torch.cuda.synchronize()
