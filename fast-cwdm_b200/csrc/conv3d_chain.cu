@@ -769,6 +769,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) conv3d_chain_kernel(cons
                     tmem_ld_x16(taddr + c0, acc);
                     tmem_ld_x16(taddr + c0 + 16, acc + 16);
                     tmem_ld_wait();
+                    if (row == 0 && c0 == col0) CHAIN_TRACE(li, 12);
                     for (int j = 0; j < s - 1; ++j) {                 // + the peers' partial sums for my columns
                         const float4* pr = reinterpret_cast<const float4*>(recv + (j * 128 + row) * (CW + 4) + (c0 - col0));
 #pragma unroll
@@ -780,6 +781,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) conv3d_chain_kernel(cons
                             acc[4 * e + 3] = __float_as_uint(__uint_as_float(acc[4 * e + 3]) + pv.w);
                         }
                     }
+                    if (row == 0 && c0 == col0) CHAIN_TRACE(li, 13);
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const int col = c0 + g * 8;

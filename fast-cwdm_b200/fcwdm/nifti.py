@@ -196,8 +196,32 @@ def encode(array, affine=None, like=None, compresslevel=1, gz=True):
     payload = build_header(a.shape, a.dtype, affine, like) + np.asfortranarray(a).tobytes(order="F")
     if not gz:
         return payload
-    co = zlib.compressobj(compresslevel, zlib.DEFLATED, 16 + zlib.MAX_WBITS)
-    return co.compress(payload) + co.flush()
+    return gzip_members(payload, compresslevel)
+
+
+_GZ_CHUNK = 4 << 20
+_gz_pool = None
+
+
+def gzip_members(payload, compresslevel=1, threads=None):
+    """gzip `payload` as a sequence of independent members of <= 4 MB, deflated concurrently (zlib releases the GIL).
+    The concatenation of gzip members is a valid gzip file (RFC 1952 section 2.2) that gzip / zlib / nibabel read as one
+    stream; a 35 MB volume costs one core ~0.35 s at level 1 as a single member and ~1/8 of that on 8 threads -- the
+    writer side of fcwdm.sample_driver was bound by exactly this."""
+    global _gz_pool
+    view = memoryview(payload)
+    if len(view) <= _GZ_CHUNK:
+        co = zlib.compressobj(compresslevel, zlib.DEFLATED, 16 + zlib.MAX_WBITS)
+        return co.compress(view) + co.flush()
+
+    def one(lo):
+        co = zlib.compressobj(compresslevel, zlib.DEFLATED, 16 + zlib.MAX_WBITS)
+        return co.compress(view[lo:lo + _GZ_CHUNK]) + co.flush()
+
+    if _gz_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _gz_pool = ThreadPoolExecutor(max_workers=threads or min(8, os.cpu_count() or 1), thread_name_prefix="fcwdm-gz")
+    return b"".join(_gz_pool.map(one, range(0, len(view), _GZ_CHUNK)))
 
 
 def write(path, array, affine=None, like=None, compresslevel=1):

@@ -526,6 +526,11 @@ class UNetTrainEngine(WavUNetTrainEngine):
     def _gn_silu(self, gn, x, N, S, silu=True):
         return self._gn_silu_t(gn, x, N, S, silu)
 
+    def _gn_silu_ssn(self, gn, x, emb_out, N, S):
+        """use_scale_shift_norm=True (unet.py:297-309; the default of the reference's model_and_diffusion_defaults): the
+        taped per-sample GroupNorm of the wavelet U-Net's training engine, keyed by the embedding slice view."""
+        return self._gn_silu_ssn_t(gn, x, self._emb_map[id(emb_out)], N, S)
+
     def _gn_silu_conv(self, gn, x, mod, N, dims, **kw):
         S = dims[0] * dims[1] * dims[2]
         return self._conv3d(mod, self._gn_silu(gn, x, N, S), N, dims, **kw)
@@ -577,9 +582,6 @@ class UNetTrainEngine(WavUNetTrainEngine):
         for mod in m.modules():
             if getattr(mod, "dropout", 0) and hasattr(mod, "in_layers"):
                 raise NotImplementedError("dropout > 0 in training is not implemented (run.sh ships dropout=0)")
-            if getattr(mod, "use_scale_shift_norm", False) and hasattr(mod, "in_layers"):
-                raise NotImplementedError("training with use_scale_shift_norm=True is not implemented (inference is; "
-                                          "run.sh trains with False)")
         N, C, D, H, W = x.shape
         dev = x.device
         with torch.cuda.device(dev):

@@ -100,6 +100,14 @@ def main():
             model.load_state_dict(owunet.seeded_state_dict(shapes, seed=0), strict=True)
             model.to(torch.device("cpu"))                  # the reference's forward asserts x.device == self.devices[0]
             one_fixture(ref, model, None, "train_unet_small.npz")
+        if "unet_ssn" in which:                                # the plain U-Net with use_scale_shift_norm=True (unet.py:297-309),
+            from oracle.make_golden_unet import UNET_SMALL_CFG   # the default of script_util.model_and_diffusion_defaults()
+            unet = importlib.import_module("guided_diffusion.unet")
+            model = unet.UNetModel(**dict(UNET_SMALL_CFG, use_scale_shift_norm=True))
+            shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+            model.load_state_dict(owunet.seeded_state_dict(shapes, seed=0), strict=True)
+            model.to(torch.device("cpu"))
+            one_fixture(ref, model, None, "train_unet_small_ssn.npz")
 
 
 if __name__ == "__main__":

@@ -174,14 +174,16 @@ def test_fused_adamw_training_reduces_loss(golden):
     assert losses[-1] < losses[0]
 
 
-def test_unet_training_step_matches_reference_fixture(golden):
+@pytest.mark.parametrize("fixture,ssn", [("train_unet_small", False), ("train_unet_small_ssn", True)])
+def test_unet_training_step_matches_reference_fixture(golden, fixture, ssn):
     """The plain UNetModel (what run.sh's training actually instantiates) under autograd: taped UNetEngine plan, zero-copy
-    concat split in the backward, avg-pool / nearest adjoints -- against the reference's own training step."""
+    concat split in the backward, avg-pool / nearest adjoints -- against the reference's own training step; also with
+    use_scale_shift_norm=True (unet.py:297-309), the default of the reference's model_and_diffusion_defaults()."""
     from guided_diffusion.script_util import create_gaussian_diffusion
     from guided_diffusion.unet import UNetModel
     from oracle.make_golden_unet import UNET_SMALL_CFG
-    g = golden("train_unet_small")
-    model = UNetModel(**UNET_SMALL_CFG)
+    g = golden(fixture)
+    model = UNetModel(**dict(UNET_SMALL_CFG, use_scale_shift_norm=ssn))
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     model.load_state_dict(ow.seeded_state_dict(shapes, seed=0), strict=True)
     model.to("cuda").train()
@@ -201,9 +203,12 @@ def test_unet_training_step_matches_reference_fixture(golden):
         if norms[name] >= 1e-3 * max(norms.values()):
             got = float(params[name].grad.double().norm())
             assert abs(got - norms[name]) <= 5e-2 * norms[name], (name, got, norms[name])
+    # stated tolerance per tensor: 8e-2; 1.2e-1 with scale-shift norm, where the worst tensors are conv biases in front of
+    # a GroupNorm (a per-channel shift is mostly cancelled by the group mean, so their gradient is the small remainder of
+    # a cancellation and carries the bf16 error of both terms: measured 9.9e-2 at cosine 0.9957); all tensors together 4e-2
     compare_grads({n: p.grad for n, p in params.items()},
                   lambda n: torch.from_numpy(g["grad/" + n]) if "grad/" + n in g.files else None, norms,
-                  "plain unet fixture (full tensors)")
+                  "plain unet fixture (full tensors)", rel_tol=1.2e-1 if ssn else 8e-2)
     sl = {n: p.grad[:2] for n, p in params.items() if "gradslice/" + n in g.files}
     sl_norms = {n: float(np.linalg.norm(g["gradslice/" + n].astype(np.float64))) for n in sl}
     # two-output-channel slices of the deepest layers (2x2x2 voxels in this fixture: GroupNorm over 8 samples amplifies the

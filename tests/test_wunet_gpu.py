@@ -239,7 +239,7 @@ def test_volume_stream_matches_direct_synthesis():
 def test_scale_shift_norm_matches_reference_fixture(golden, which):
     """use_scale_shift_norm=True (the default of the reference's model_and_diffusion_defaults; run.sh passes False):
     out_norm(h) * (1 + scale) + shift with (scale, shift) = chunk(emb_out, 2) (wunet.py:256-260, unet.py:301-305), against
-    a forward of the unmodified reference (oracle/make_golden_ssn.py).  Inference only: training refuses the flag."""
+    a forward of the unmodified reference (oracle/make_golden_ssn.py), in inference and in the taped training forward."""
     from oracle.make_golden_unet import UNET_SMALL_CFG
     if which == "wunet":
         from guided_diffusion.wunet import WavUNetModel as Model
@@ -266,13 +266,9 @@ def test_scale_shift_norm_matches_reference_fixture(golden, which):
     assert rel <= 3e-2 and psnr(y, ref) >= 40.0
     m.train()
     x = torch.from_numpy(g["x"]).cuda()
-    if which == "unet":
-        with pytest.raises(NotImplementedError):
-            m(x, torch.from_numpy(g["t"]).cuda())
-    else:
-        out = m(x, torch.from_numpy(g["t"]).cuda())              # taped forward (gradients: tests/test_train_gpu.py)
-        assert out.requires_grad and out.shape == ref.shape
-        assert float((out.detach().cpu() - ref).norm() / ref.norm()) <= 3e-2
+    out = m(x, torch.from_numpy(g["t"]).cuda())                  # taped forward, both models (gradients: tests/test_train_gpu.py)
+    assert out.requires_grad and out.shape == ref.shape
+    assert float((out.detach().cpu() - ref).norm() / ref.norm()) <= 3e-2
 
 
 def test_scale_shift_norm_under_the_graph_sampler(monkeypatch):

@@ -14,7 +14,7 @@ from fcwdm import native, ops  # noqa: E402
 import chain_probe as cp  # noqa: E402  (prints its own table first)
 
 NAMES = ["A prod at layer", "barrier passed", "sgn ready", "plane0 landed", "plane0 handed", "first MMA", "last MMA issued",
-         "acc complete", "exchanged", "stored", "stats flushed", "arrived"]
+         "acc complete", "exchanged", "stored", "stats flushed", "arrived", "chunk0 tmem", "chunk0 +partials"]
 dev = torch.device("cuda")
 for name, N, dims, widths in (("7^3 256 x6", 1, (5, 7, 7), (256,) * 7), ("14^3 256 x6", 1, (10, 14, 14), (256,) * 7),
                               ("28^3 128 x6", 1, (20, 28, 28), (128,) * 7)):
