@@ -212,10 +212,27 @@ def test_trainloop_matches_three_steps_of_the_unmodified_reference(tmp_path, mon
             assert err <= 0.25, (k, err)     # Adam normalises |g| away: sign flips of near-zero bf16 gradients dominate (measured 2e-3 .. 1.6e-1)
         names = list(g["param_names"])
         num = den = 0.0
+        # Adam divides by |g|: a tensor whose true gradient is ZERO gets updates of lr * g / eps -> ~0 in fp32 (|g| ~ 1e-10
+        # << eps) but full lr-sized steps from bf16 rounding noise (|g| ~ 1e-6 >> eps).  This small model has ONE channel per
+        # GroupNorm group, so every per-channel shift in front of a GroupNorm (the timestep projection emb_layers.1 and the
+        # bias of in_layers.2) is removed exactly by the group mean and has no effect on the loss; such tensors are
+        # recognised by the reference's own update being far below the full Adam step (lr per element per step) and left
+        # out of the size comparison (CFG-W4 has 2+ channels per group: no such tensors there)
+        contrib, skipped = [], []
+        shapes = {k: v.numel() for k, v in start.items()}
         for k, ref_n in zip(names, g["param_delta_norms"]):
             d = float((final[k] - start[k]).double().norm())
+            full_step = 1e-3 * shapes[k] ** 0.5                      # one lr-sized Adam step on every element
+            if float(ref_n) < 0.2 * full_step and (".emb_layers.1." in k or k.endswith("in_layers.2.bias")):
+                skipped.append(k)
+                continue
             num += (d - ref_n) ** 2
             den += ref_n ** 2
+            contrib.append(((d - ref_n) ** 2, k, d, float(ref_n)))
+        for c, k, d, r in sorted(contrib, reverse=True)[:5]:
+            print(f"update norm of {k}: {d:.4e} reference {r:.4e}")
+        print(f"update norms over {len(contrib)} tensors: rel {(num / den) ** 0.5:.3e}; {len(skipped)} zero-gradient tensors skipped")
+        assert len(contrib) >= 0.7 * len(names)
         assert (num / den) ** 0.5 <= 5e-2                                            # size of every tensor's update
     finally:
         logger.reset()
