@@ -508,6 +508,11 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
                                 acc[e] = __float_as_uint(__uint_as_float(acc[e]) + pr[(c0 + e) * 128]);
                         }
                     }
+                    // statistics: one warp reduction per 32 columns where the group width allows (conv3d_gn.cuh)
+                    const bool chunk_stats = want_stats && (COLS % 32 == 0) && gn_chunk_ok(args.gn_cpg);
+                    float ca[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) ca[e] = 0.f;
 #pragma unroll
                     for (int g = 0; g < COLS / 8; ++g) {
                         const int col = c0 + g * 8;
@@ -535,13 +540,21 @@ __global__ void __launch_bounds__(GN_IN ? 384 : 256, 1) conv3d_igemm_kernel(cons
 #pragma unroll
                                     for (int e = 0; e < 8; ++e) vr[e] = 0.f;
                                 }
-                                switch (args.gn_cpg) {
+                                if (chunk_stats) {
+                                    gn_chunk_add(ca, g & 3, vr);
+                                } else switch (args.gn_cpg) {
                                     case 1: gn_accumulate<1>(vr, my_stat, co, lane); break;
                                     case 2: gn_accumulate<2>(vr, my_stat, co, lane); break;
                                     case 4: gn_accumulate<4>(vr, my_stat, co, lane); break;
                                     default: gn_accumulate_wide(vr, my_stat, co / args.gn_cpg, lane); break;
                                 }
                             }
+                        }
+                        if ((g & 3) == 3 && chunk_stats) {                      // a 32-column chunk is complete
+                            const int ch0 = tc.n0 + c0 + (g - 3) * 8;
+                            if (ch0 < args.Cout) gn_chunk_flush(ca, my_stat, ch0, args.gn_cpg, lane);
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) ca[e] = 0.f;
                         }
                     }
                 }

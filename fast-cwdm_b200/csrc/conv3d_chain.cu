@@ -782,6 +782,11 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) conv3d_chain_kernel(cons
                         }
                     }
                     if (row == 0 && c0 == col0) CHAIN_TRACE(li, 13);
+                    // statistics: one warp reduction per 32-column chunk (conv3d_gn.cuh)
+                    const bool chunk_stats = want_stats && gn_chunk_ok(L.gn_cpg);
+                    float ca[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) ca[e] = 0.f;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const int col = c0 + g * 8;
@@ -801,17 +806,25 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) conv3d_chain_kernel(cons
                                 for (int e = 0; e < 8; ++e) v[e] += rr[e];
                             }
                             const uint4 packed = pack8(v);
+#if !(defined(FCWDM_CHAIN_EXP) && (FCWDM_CHAIN_EXP & 2))
                             if (ok) *reinterpret_cast<uint4*>(L.y + vox * L.y_ld + co) = packed;
+#endif
                             if (use_res && c0 + 32 < col0 + CW && co + 32 < L.Cout)   // next 32 columns' residual, one chunk ahead
                                 res[g] = ld_cg_u4(L.residual + vox * L.res_ld + co + 32);
+#if defined(FCWDM_CHAIN_EXP) && (FCWDM_CHAIN_EXP & 1)
+                            if (want_stats && packed.x == 0x12345678u) {
+#else
                             if (want_stats) {                          // statistics of the STORED (bf16) values
+#endif
                                 float vr[8];
                                 unpack8(packed, vr);
                                 if (!ok) {
 #pragma unroll
                                     for (int e = 0; e < 8; ++e) vr[e] = 0.f;
                                 }
-                                switch (L.gn_cpg) {
+                                if (chunk_stats) {
+                                    gn_chunk_add(ca, g, vr);
+                                } else switch (L.gn_cpg) {
                                     case 1: gn_accumulate<1>(vr, my_stat, co, lane); break;
                                     case 2: gn_accumulate<2>(vr, my_stat, co, lane); break;
                                     case 4: gn_accumulate<4>(vr, my_stat, co, lane); break;
@@ -820,6 +833,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) conv3d_chain_kernel(cons
                             }
                         }
                     }
+                    if (chunk_stats && tc.n0 + c0 < L.Cout) gn_chunk_flush(ca, my_stat, tc.n0 + c0, L.gn_cpg, lane);
                 }
                 tc_fence_before();
                 __syncwarp();

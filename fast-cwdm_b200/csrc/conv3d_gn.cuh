@@ -57,6 +57,47 @@ __device__ __forceinline__ void gn_accumulate_wide(const float* vr, float* my_st
     }
     warp_reduce_scatter<2>(a, lane, my_stat + 2 * grp);
 }
+// ---- statistics of a 32-column chunk with ONE warp reduction --------------------------------------------
+// One reduce per 8 columns (above) is a dependent chain of ~6 shuffles + a shared-memory update, 16 times per 128-column
+// row: ~2.7 us per tile on an epilogue warp that has its scheduler to itself.  Here the lane first adds up (sum, sum of
+// squares) of every 4-column run of a 32-column chunk in registers -- ca[16], run r at ca[2r], ca[2r+1] -- and the warp
+// reduces once per chunk.  Supported channels per group: 4, 8, 16 and multiples of 32 (gn_chunk_ok).
+__device__ __forceinline__ bool gn_chunk_ok(int cpg) { return cpg == 4 || cpg == 8 || cpg == 16 || (cpg > 0 && (cpg & 31) == 0); }
+// vr: the 8 stored values of columns [8 g4, 8 g4 + 8) of the chunk (g4 = 0..3, compile-time after unrolling)
+__device__ __forceinline__ void gn_chunk_add(float* ca, int g4, const float* vr) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        ca[4 * g4] += vr[e];
+        ca[4 * g4 + 1] = fmaf(vr[e], vr[e], ca[4 * g4 + 1]);
+        ca[4 * g4 + 2] += vr[4 + e];
+        ca[4 * g4 + 3] = fmaf(vr[4 + e], vr[4 + e], ca[4 * g4 + 3]);
+    }
+}
+// ch0: absolute channel of the chunk's first column (a multiple of 32); my_stat: this warp's [group][2] row; ca is consumed
+__device__ __forceinline__ void gn_chunk_flush(float* ca, float* my_stat, int ch0, int cpg, int lane) {
+    if (cpg == 4) {
+        warp_reduce_scatter<16>(ca, lane, my_stat + 2 * (ch0 >> 2));
+        return;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {                                   // 8-column runs
+        ca[2 * g] = ca[4 * g] + ca[4 * g + 2];
+        ca[2 * g + 1] = ca[4 * g + 1] + ca[4 * g + 3];
+    }
+    if (cpg == 8) {
+        warp_reduce_scatter<8>(ca, lane, my_stat + 2 * (ch0 >> 3));
+        return;
+    }
+    ca[0] += ca[2]; ca[1] += ca[3];                                 // 16-column runs
+    ca[2] = ca[4] + ca[6]; ca[3] = ca[5] + ca[7];
+    if (cpg == 16) {
+        warp_reduce_scatter<4>(ca, lane, my_stat + 2 * (ch0 >> 4));
+        return;
+    }
+    ca[0] += ca[2]; ca[1] += ca[3];                                 // 32 or more channels per group: one group per chunk
+    warp_reduce_scatter<2>(ca, lane, my_stat + 2 * (ch0 / cpg));
+}
+
 __device__ __forceinline__ float c_silu(float x) {
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));

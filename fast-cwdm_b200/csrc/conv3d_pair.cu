@@ -155,8 +155,17 @@ __device__ __forceinline__ float p_silu(float x) {
 
 constexpr int kPWarpProdA = 4, kPWarpProdB = 5, kPWarpAlloc = 6, kPWarpMma = 7;
 
+// Transform (fused GroupNorm + SiLU) warps of the GN_IN variant.  A plane costs them ~1.6 us with 4 warps: hidden behind the
+// 36 N = 192 MMAs of a 64-channel layer (1.8 us), but twice the ~0.9 us the 36 N = 48 MMAs of the output conv (C_out = 8,
+// N_TILE = 16) take -- that layer was transform-bound (104 us for 28 GFLOP); its small epilogue leaves the registers for 8.
 template <int N_TILE, bool GN_IN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1)
+struct PairXf {
+    static constexpr int WARPS = GN_IN ? (N_TILE == 16 ? 8 : 4) : 0;
+    static constexpr int THREADS = WARPS * 32;
+};
+
+template <int N_TILE, bool GN_IN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256 + PairXf<N_TILE, GN_IN>::THREADS, 1)
     conv3d_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const PairArgs args) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -187,7 +196,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::A_SLOTS; ++i) {
-            mbar_init(full_a + 8 * i, GN_IN ? 8 : 1);   // GN_IN: 4 producer warps x 2 CTAs arrive remotely
+            mbar_init(full_a + 8 * i, GN_IN ? 2 * PairXf<N_TILE, GN_IN>::WARPS : 1);   // GN_IN: transform warps x 2 CTAs arrive remotely
             mbar_init(empty_a + 8 * i, 1);
             mbar_init(landed_a + 8 * i, 1);
         }
@@ -210,8 +219,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Register rebalancing (GN_IN, 64 channels: 384 threads are capped at 168 registers each): the four single-lane control
+    // warps hand most of theirs to the epilogue warps, which then hold a whole residual row one plane ahead.
+    // Compile-time experiments, OFF by default (measured on B200, same-box A/B, round 2): giving the epilogue warps the
+    // control warps' registers with setmaxnreg (232 / 96 / 168 per thread) and holding a whole residual row one plane ahead
+    // made BOTH in-step forms ~18 us slower (141 -> 160 us, 163 -> 183 us): the MMA-issuing warp spills below 168 registers.
+#ifdef FCWDM_PAIR_REBALANCE_INC
+    constexpr bool REBALANCE = GN_IN && N_TILE == 64;
+#else
+    constexpr bool REBALANCE = false;
+#define FCWDM_PAIR_REBALANCE_INC 232
+#define FCWDM_PAIR_REBALANCE_DEC 96
+#endif
+#ifdef FCWDM_PAIR_RES_AHEAD
+    constexpr bool RES_AHEAD = N_TILE == 64;
+#else
+    constexpr bool RES_AHEAD = false;
+#endif
 
-    if (warp == kPWarpProdB) {
+    if (warp >= 4 && warp < 8) {
+      // the control warpgroup (one ptxas region, so the smaller register budget applies to exactly this code)
+      if constexpr (REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FCWDM_PAIR_REBALANCE_DEC));
+      if (warp == kPWarpProdB) {
         // ============ resident weights: this CTA's half (NF/2 rows) of all 9 filter columns, loaded once ============
         if (lane == 0) {
             if (leader) mbar_arrive_expect_tx(b_full, 2 * Cfg::B_BYTES);
@@ -241,95 +270,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
                 }
             }
         }
-    } else if (GN_IN && warp >= 8) {
-        // ============ A producers with fused GroupNorm + SiLU (4 warps): global -> registers -> normalise, activate ->
-        // swizzled shared memory (the layout TMA SWIZZLE_128B would have produced).  Out-of-range halo voxels are
-        // written as ZERO: the convolution pads the ACTIVATED tensor.  ============
-        const int pt = threadIdx.x - 256;                       // 0..127
-        const uint32_t full_a_leader = mapa_u32(full_a, 0);
-        constexpr int CHUNKS = Cfg::HROWS * Cfg::ROWP * 8;       // 16-byte chunks per plane (1440)
-        constexpr int PER_THREAD = (CHUNKS + 127) / 128;         // 12
-        const int jmine = (pt & 7) ^ ((pt >> 3) & 7);
-        float sc[8], sh[8];
-        int cur_n = -1;
-        uint32_t J = 0;
-        for (int item = cluster_id; item < args.num_items; item += num_clusters) {
-            const PairItem it = decode_item(item, args, (int)rank);
-            if (it.n != cur_n) {
-                cur_n = it.n;
-                asm volatile("bar.sync 2, 128;" ::: "memory");
-                if (pt < 64) {
-                    float sc0 = 0.f, sh0 = 0.f;
-                    if (pt < args.Cin) {
-                        const int cpg = args.Cin / args.gi_groups;
-                        const int g = pt / cpg;
-                        double sum = 0.0, sq = 0.0;
-                        for (int r = 0; r < FCWDM_GN_STAT_REPLICAS; ++r) {
-                            const double* sp = args.gi_stats + (((long long)it.n * FCWDM_GN_STAT_REPLICAS + r) * args.gi_groups + g) * 2;
-                            sum += sp[0];
-                            sq += sp[1];
-                        }
-                        const double cnt = (double)args.D * args.H * args.W * cpg;
-                        const double mean = sum / cnt;
-                        double var = sq / cnt - mean * mean;
-                        var = var < 0.0 ? 0.0 : var;
-                        const float rstd = (float)(1.0 / sqrt(var + (double)args.gi_eps));
-                        sc0 = rstd * __ldg(args.gi_gamma + pt);
-                        sh0 = __ldg(args.gi_beta + pt) - (float)mean * sc0;
-                    }
-                    sgn[pt] = sc0;
-                    sgn[64 + pt] = sh0;
-                }
-                asm volatile("bar.sync 2, 128;" ::: "memory");
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    sc[e] = sgn[jmine * 8 + e];
-                    sh[e] = sgn[64 + jmine * 8 + e];
-                }
-            }
-            for (int k = 0; k < it.L + 2; ++k, ++J) {
-                const uint32_t slot = J % Cfg::A_SLOTS, use = J / Cfg::A_SLOTS;
-                const int d = it.d_begin - 1 + k;
-                const bool d_ok = (d >= 0) && (d < args.D);
-                mbar_wait(landed_a + 8 * slot, use & 1);          // TMA has written the raw plane (zeros out of range)
-                const uint32_t base = smem_a + slot * Cfg::SLOT_BYTES;
-                if (d_ok) {
-                    // all shared-memory loads first (independent, pipelined), then the arithmetic and the stores:
-                    // a load -> compute -> store chain per chunk is latency-bound (~450 cycles per chunk)
-                    uint4* plane = reinterpret_cast<uint4*>(smem_raw + (base - smem_u32(smem_raw)));
-                    uint4 raw[PER_THREAD];
-                    uint32_t valid = 0;
-#pragma unroll
-                    for (int q = 0; q < PER_THREAD; ++q) {
-                        const int c = pt + q * 128;
-                        const int r = c >> 3;
-                        const int hr = r / Cfg::ROWP, wc = r - hr * Cfg::ROWP;
-                        const int h = it.h0 - 1 + hr, w = it.w0 - 1 + wc;
-                        // out-of-range halo voxels stay ZERO: the convolution pads the ACTIVATED tensor
-                        const bool in = (c < CHUNKS) && (h >= 0) && (h < args.H) && (w >= 0) && (w < args.W);
-                        raw[q] = make_uint4(0u, 0u, 0u, 0u);
-                        if (in) {
-                            raw[q] = plane[c];
-                            valid |= 1u << q;
-                        }
-                    }
-                    // this thread's logical 16-byte chunk index is the same for all of its chunks
-                    // (c = pt + 128 q  =>  (c & 7) ^ ((c >> 3) & 7) does not depend on q): scale / shift live in registers
-#pragma unroll
-                    for (int q = 0; q < PER_THREAD; ++q) {
-                        float f[8];
-                        unpack8(raw[q], f);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = p_silu(fmaf(f[e], sc[e], sh[e]));
-                        if (valid & (1u << q)) plane[pt + q * 128] = pack8(f);
-                    }
-                }
-                fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(full_a_leader + 8 * slot);
-            }
-        }
-    } else if (warp == kPWarpMma) {
+      } else if (warp == kPWarpMma) {
         // ============ MMA issuer (leader CTA only) ============
         if (leader) {
             // M = 256 (m_dim = 16), N = NF, bf16 x bf16 -> f32, K-major A and B
@@ -390,8 +331,99 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
                 G += it.L + 4;
             }
         }
+      }
+    } else if (GN_IN && warp >= 8) {
+        // ============ A producers with fused GroupNorm + SiLU (4 warps): global -> registers -> normalise, activate ->
+        // swizzled shared memory (the layout TMA SWIZZLE_128B would have produced).  Out-of-range halo voxels are
+        // written as ZERO: the convolution pads the ACTIVATED tensor.  ============
+        constexpr int XFT = GN_IN ? PairXf<N_TILE, GN_IN>::THREADS : 128;   // 128, or 256 for the output conv (branch dead without GN_IN)
+        const int pt = threadIdx.x - 256;                       // 0..XFT-1
+        const uint32_t full_a_leader = mapa_u32(full_a, 0);
+        constexpr int CHUNKS = Cfg::HROWS * Cfg::ROWP * 8;       // 16-byte chunks per plane (1440)
+        constexpr int PER_THREAD = (CHUNKS + XFT - 1) / XFT;     // 12 (6)
+        const int jmine = (pt & 7) ^ ((pt >> 3) & 7);
+        float sc[8], sh[8];
+        int cur_n = -1;
+        uint32_t J = 0;
+        for (int item = cluster_id; item < args.num_items; item += num_clusters) {
+            const PairItem it = decode_item(item, args, (int)rank);
+            if (it.n != cur_n) {
+                cur_n = it.n;
+                asm volatile("bar.sync 2, %0;" ::"n"(XFT) : "memory");
+                if (pt < 64) {
+                    float sc0 = 0.f, sh0 = 0.f;
+                    if (pt < args.Cin) {
+                        const int cpg = args.Cin / args.gi_groups;
+                        const int g = pt / cpg;
+                        double sum = 0.0, sq = 0.0;
+                        for (int r = 0; r < FCWDM_GN_STAT_REPLICAS; ++r) {
+                            const double* sp = args.gi_stats + (((long long)it.n * FCWDM_GN_STAT_REPLICAS + r) * args.gi_groups + g) * 2;
+                            sum += sp[0];
+                            sq += sp[1];
+                        }
+                        const double cnt = (double)args.D * args.H * args.W * cpg;
+                        const double mean = sum / cnt;
+                        double var = sq / cnt - mean * mean;
+                        var = var < 0.0 ? 0.0 : var;
+                        const float rstd = (float)(1.0 / sqrt(var + (double)args.gi_eps));
+                        sc0 = rstd * __ldg(args.gi_gamma + pt);
+                        sh0 = __ldg(args.gi_beta + pt) - (float)mean * sc0;
+                    }
+                    sgn[pt] = sc0;
+                    sgn[64 + pt] = sh0;
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(XFT) : "memory");
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    sc[e] = sgn[jmine * 8 + e];
+                    sh[e] = sgn[64 + jmine * 8 + e];
+                }
+            }
+            for (int k = 0; k < it.L + 2; ++k, ++J) {
+                const uint32_t slot = J % Cfg::A_SLOTS, use = J / Cfg::A_SLOTS;
+                const int d = it.d_begin - 1 + k;
+                const bool d_ok = (d >= 0) && (d < args.D);
+                mbar_wait(landed_a + 8 * slot, use & 1);          // TMA has written the raw plane (zeros out of range)
+                const uint32_t base = smem_a + slot * Cfg::SLOT_BYTES;
+                if (d_ok) {
+                    // all shared-memory loads first (independent, pipelined), then the arithmetic and the stores:
+                    // a load -> compute -> store chain per chunk is latency-bound (~450 cycles per chunk)
+                    uint4* plane = reinterpret_cast<uint4*>(smem_raw + (base - smem_u32(smem_raw)));
+                    uint4 raw[PER_THREAD];
+                    uint32_t valid = 0;
+#pragma unroll
+                    for (int q = 0; q < PER_THREAD; ++q) {
+                        const int c = pt + q * XFT;
+                        const int r = c >> 3;
+                        const int hr = r / Cfg::ROWP, wc = r - hr * Cfg::ROWP;
+                        const int h = it.h0 - 1 + hr, w = it.w0 - 1 + wc;
+                        // out-of-range halo voxels stay ZERO: the convolution pads the ACTIVATED tensor
+                        const bool in = (c < CHUNKS) && (h >= 0) && (h < args.H) && (w >= 0) && (w < args.W);
+                        raw[q] = make_uint4(0u, 0u, 0u, 0u);
+                        if (in) {
+                            raw[q] = plane[c];
+                            valid |= 1u << q;
+                        }
+                    }
+                    // this thread's logical 16-byte chunk index is the same for all of its chunks
+                    // (c = pt + XFT q, XFT a multiple of 64  =>  (c & 7) ^ ((c >> 3) & 7) does not depend on q): scale / shift live in registers
+#pragma unroll
+                    for (int q = 0; q < PER_THREAD; ++q) {
+                        float f[8];
+                        unpack8(raw[q], f);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = p_silu(fmaf(f[e], sc[e], sh[e]));
+                        if (valid & (1u << q)) plane[pt + q * XFT] = pack8(f);
+                    }
+                }
+                fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(full_a_leader + 8 * slot);
+            }
+        }
     } else if (warp < 4) {
         // ============ epilogue: this CTA's 128 accumulator lanes ============
+        if constexpr (REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FCWDM_PAIR_REBALANCE_INC));
         const int ew = warp;
         const int row = ew * 32 + lane;
         const int hh = row >> 3, ww = row & 7;
@@ -414,6 +446,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
         int cur_n = -1;
         uint32_t G = 0;
         constexpr int HALF = N_TILE < 32 ? N_TILE : 32;          // accumulator columns drained per batch of TMEM loads
+        uint4 res_next[N_TILE / 8];                              // RES_AHEAD: the next plane's residual row
+#pragma unroll
+        for (int g = 0; g < N_TILE / 8; ++g) res_next[g] = make_uint4(0u, 0u, 0u, 0u);
         for (int item = cluster_id; item < args.num_items; item += num_clusters) {
             const PairItem it = decode_item(item, args, (int)rank);
             if (it.n != cur_n) {
@@ -444,13 +479,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
                 const bool ok = real && hw_ok;
                 const bool use_res = ok && args.residual != nullptr;
                 const long long vox = (((long long)it.n * args.D + d) * args.H + h) * args.W + w;
-                // the NEXT plane's residual row (one 128-byte line per thread) is pulled into L2 now, so that its loads one
-                // plane later are L2 hits instead of HBM round trips (the epilogue has ~1.7 us per plane)
-                if (args.residual != nullptr && hw_ok && d + 1 >= 0 && d + 1 < args.D)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(args.residual + (vox + (long long)args.H * args.W) * args.res_ld));
-                // first half of the residual row: in flight while we wait for the accumulator
-                uint4 res[HALF / 8];
-                if (use_res) {
+                // the residual row (one 128-byte line per thread) of a LATER plane is pulled into L2 now, so that its loads
+                // are L2 hits instead of HBM round trips (the epilogue has ~1.7 us per plane)
+                constexpr int PF = RES_AHEAD ? 2 : 1;
+                if (args.residual != nullptr && hw_ok && d + PF >= 0 && d + PF < args.D)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(args.residual + (vox + (long long)PF * args.H * args.W) * args.res_ld));
+                uint4 res[RES_AHEAD ? N_TILE / 8 : HALF / 8];
+                if constexpr (RES_AHEAD) {
+                    // whole rows, one plane ahead: this plane's row was requested a plane ago (or right here for the first
+                    // plane of an item), the next plane's row goes out now and lands while this plane is drained and stored
+                    if (use_res && i == 2) {
+#pragma unroll
+                        for (int g = 0; g < N_TILE / 8; ++g)
+                            if (g * 8 < args.Cout) res_next[g] = *reinterpret_cast<const uint4*>(args.residual + vox * args.res_ld + g * 8);
+                    }
+#pragma unroll
+                    for (int g = 0; g < N_TILE / 8; ++g) res[g] = res_next[g];
+                    if (args.residual != nullptr && hw_ok && i + 1 >= 2 && i + 1 < it.L + 2) {
+                        const __nv_bfloat16* rn = args.residual + (vox + (long long)args.H * args.W) * args.res_ld;
+#pragma unroll
+                        for (int g = 0; g < N_TILE / 8; ++g)
+                            if (g * 8 < args.Cout) res_next[g] = *reinterpret_cast<const uint4*>(rn + g * 8);
+                    }
+                } else if (use_res) {
+                    // first half of the residual row: in flight while we wait for the accumulator
 #pragma unroll
                     for (int g = 0; g < HALF / 8; ++g)
                         if (g * 8 < args.Cout) res[g] = *reinterpret_cast<const uint4*>(args.residual + vox * args.res_ld + g * 8);
@@ -499,7 +551,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
                                 vv[6] = __uint_as_float(acc[g * 8 + 6]) + b1.z; vv[7] = __uint_as_float(acc[g * 8 + 7]) + b1.w;
                                 if (use_res) {
                                     float rr[8];
-                                    unpack8(res[g], rr);
+                                    unpack8(res[RES_AHEAD ? (c0 / 8 + g) : g], rr);
 #pragma unroll
                                     for (int e = 0; e < 8; ++e) vv[e] += rr[e];
                                 }
@@ -516,7 +568,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN_IN ? 384 : 256, 1
                                 }
                             }
                         }
-                        if (use_res && c0 + HALF < N_TILE) {              // next half of the residual row
+                        if (!RES_AHEAD && use_res && c0 + HALF < N_TILE) {   // next half of the residual row
 #pragma unroll
                             for (int g = 0; g < HALF / 8; ++g)
                                 if (c0 + HALF + g * 8 < args.Cout)
@@ -592,7 +644,7 @@ static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const PairA
     const int grid = 2 * (a.num_items < clusters ? a.num_items : clusters);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(GN_IN ? 384 : 256);
+    cfg.blockDim = dim3(256 + PairXf<N_TILE, GN_IN>::THREADS);
     cfg.dynamicSmemBytes = PairCfg<N_TILE>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

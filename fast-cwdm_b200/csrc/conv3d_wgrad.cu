@@ -723,48 +723,62 @@ struct PackJob {            // mirrored by fcwdm/engine.py (8 x int64)
 constexpr int kPackPairs = 512;
 constexpr int kPackTapsMax = 27;
 
-__global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict__ jobs) {
-    pdl_prologue();
-    __shared__ __nv_bfloat16 tile[kPackPairs * kPackTapsMax];
-    const PackJob j = jobs[blockIdx.y];
-    const int O = (int)j.O, I = (int)j.I, taps = (int)j.taps;
+// TAPS and the tile shape are compile-time so that every index split below divides by a constant (the generic form spent
+// most of its time in 32-bit integer division: 0.55 ms for the 0.65 GB it moves)
+template <int TAPS, bool TRANSPOSED>
+__device__ __forceinline__ void pack_job_tiles(const PackJob& j, __nv_bfloat16* tile) {
+    const int O = (int)j.O, I = (int)j.I;
     const int O_p = j.pair ? (O <= 16 ? 16 : 64) : (O + 15) / 16 * 16;
     const int I_p = j.pair ? 64 : (I + 63) / 64 * 64;
-    const int TO = j.transposed ? 16 : 8, TI = kPackPairs / TO;
+    constexpr int TO = TRANSPOSED ? 16 : 8, TI = kPackPairs / TO;
+    constexpr int RUN = (TRANSPOSED ? TO : TI) * TAPS;            // source elements that are contiguous per source row
     const int tiles_i = (I_p + TI - 1) / TI, tiles_o = (O_p + TO - 1) / TO;
-    const int run = (j.transposed ? TO : TI) * taps;              // source elements that are contiguous per source row
+    const bool pair = j.pair != 0;
     for (int t = blockIdx.x; t < tiles_o * tiles_i; t += gridDim.x) {
         const int o0 = (t / tiles_i) * TO, i0 = (t % tiles_i) * TI;
         __syncthreads();                                          // the previous tile has been written out
-        for (int e = threadIdx.x; e < kPackPairs * taps; e += blockDim.x) {
-            const int row = e / run, rem = e - row * run;         // source row inside the tile, offset inside its run
-            const int col = rem / taps, tap = rem - col * taps;
+#pragma unroll 4
+        for (int e = threadIdx.x; e < kPackPairs * TAPS; e += 256) {
+            const int row = e / RUN, rem = e - row * RUN;         // source row inside the tile, offset inside its run
+            const int col = rem / TAPS, tap = rem - col * TAPS;
             float v = 0.f;
             int o_l, i_l, tap_d;
-            if (j.transposed) {                                   // w'[o][i][tap] = w[i][o][taps - 1 - tap]
-                i_l = row; o_l = col; tap_d = taps - 1 - tap;
-                if (i0 + i_l < I && o0 + o_l < O) v = j.src[((long long)(i0 + i_l) * O + o0) * taps + rem];
+            if (TRANSPOSED) {                                     // w'[o][i][tap] = w[i][o][taps - 1 - tap]
+                i_l = row; o_l = col; tap_d = TAPS - 1 - tap;
+                if (i0 + i_l < I && o0 + o_l < O) v = __ldg(j.src + ((long long)(i0 + i_l) * O + o0) * TAPS + rem);
             } else {
                 o_l = row; i_l = col; tap_d = tap;
-                if (o0 + o_l < O && i0 + i_l < I) v = j.src[((long long)(o0 + o_l) * I + i0) * taps + rem];
+                if (o0 + o_l < O && i0 + i_l < I) v = __ldg(j.src + ((long long)(o0 + o_l) * I + i0) * TAPS + rem);
             }
-            tile[(o_l * TI + i_l) * taps + tap_d] = __float2bfloat16_rn(v);
+            tile[(o_l * TI + i_l) * TAPS + tap_d] = __float2bfloat16_rn(v);
         }
         __syncthreads();
-        for (int f = threadIdx.x; f < kPackPairs * taps; f += blockDim.x) {
+#pragma unroll 4
+        for (int f = threadIdx.x; f < kPackPairs * TAPS; f += 256) {
             const int tap = f / kPackPairs, p = f - tap * kPackPairs;
             const int o = o0 + p / TI, i = i0 + p % TI;
             if (o < O_p && i < I_p) {
                 long long idx;
-                if (j.pair) {
+                if (pair) {
                     const int kd = tap / 9, t2 = tap - kd * 9;    // pair layout: [kh*3+kw][kd][O_p][64]
                     idx = (((long long)t2 * 3 + kd) * O_p + o) * 64 + i;
                 } else {
                     idx = ((long long)tap * O_p + o) * I_p + i;
                 }
-                j.dst[idx] = tile[p * taps + tap];
+                j.dst[idx] = tile[p * TAPS + tap];
             }
         }
+    }
+}
+
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict__ jobs) {
+    pdl_prologue();
+    __shared__ __nv_bfloat16 tile[kPackPairs * kPackTapsMax];
+    const PackJob j = jobs[blockIdx.y];
+    if (j.taps == 27) {
+        if (j.transposed) pack_job_tiles<27, true>(j, tile); else pack_job_tiles<27, false>(j, tile);
+    } else {
+        if (j.transposed) pack_job_tiles<1, true>(j, tile); else pack_job_tiles<1, false>(j, tile);
     }
 }
 

@@ -127,7 +127,9 @@ __global__ void __launch_bounds__(kTrThreads) gn_bwd_reduce_kernel(const __nv_bf
 
 // pass 2: dx = rstd * (gamma * dz - (S1 + x_hat * S2) / M) (+ acc), S1 = sum_{c in group} gamma_c A_c,
 // S2 = sum gamma_c B_c, M = S * channels_per_group; block (0, n) also adds A, B into dbeta, dgamma.
-template <bool kSilu>
+// kColsum: also cs[n][c] += sum_v dx[n,v,c] over the STORED (bf16) values -- the bias / timestep-embedding gradient of the
+// conv that produced x, which otherwise costs fcwdm_colsum_cl one more pass over dx.
+template <bool kSilu, bool kColsum>
 __global__ void __launch_bounds__(kTrThreads, 2) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_ld,
                                                                   const __nv_bfloat16* __restrict__ dy, int64_t dy_ld,
                                                                   const double* __restrict__ stats,
@@ -137,9 +139,11 @@ __global__ void __launch_bounds__(kTrThreads, 2) gn_bwd_apply_kernel(const __nv_
                                                                   const __nv_bfloat16* __restrict__ acc, int64_t acc_ld,
                                                                   __nv_bfloat16* __restrict__ dx, int64_t dx_ld,
                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                  float* __restrict__ cs, int64_t cs_ld,
                                                                   int64_t S, int C, int G, float eps) {
     pdl_prologue();
     extern __shared__ float sm[];   // [7][C]: xs, xh, gam, bet, k2, k3, scratch(gamma*A) ; scratch2 (gamma*B) at [7]
+                                    // kColsum: reused as [8][blockDim] partial column sums at the end
     const int n = blockIdx.y;
     const int cpg = C / G;
     const double cnt = (double)S * (double)cpg;
@@ -198,6 +202,9 @@ __global__ void __launch_bounds__(kTrThreads, 2) gn_bwd_apply_kernel(const __nv_
     const __nv_bfloat16* ab = acc ? acc + (int64_t)n * S * acc_ld + chunk * 8 : nullptr;
     __nv_bfloat16* ob = dx + (int64_t)n * S * dx_ld + chunk * 8;
     const int64_t stride = (int64_t)gridDim.x * vpb;
+    float csum[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) csum[j] = 0.f;
     auto apply = [&](const uint4& ux, const uint4& ud, const uint4& ua, int64_t v) {
         float fx[8], fd[8], fa[8];
         unpack8(ux, fx);
@@ -216,7 +223,13 @@ __global__ void __launch_bounds__(kTrThreads, 2) gn_bwd_apply_kernel(const __nv_
             if (ab != nullptr) o += fa[j];
             fd[j] = o;
         }
-        st_stream_u4(ob + v * dx_ld, pack8(fd));
+        const uint4 packed = pack8(fd);
+        st_stream_u4(ob + v * dx_ld, packed);
+        if (kColsum) {
+            unpack8(packed, fd);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) csum[j] += fd[j];
+        }
     };
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
     int64_t v = (int64_t)blockIdx.x * vpb + lane;
@@ -234,6 +247,35 @@ __global__ void __launch_bounds__(kTrThreads, 2) gn_bwd_apply_kernel(const __nv_
     for (; v < S; v += stride)
         apply(ld_stream_u4(xb + v * x_ld), ld_stream_u4(db + v * dy_ld),
               ab != nullptr ? ld_stream_u4(ab + v * acc_ld) : zero4, v);
+    if (kColsum) {
+        __syncthreads();                                   // the coefficient table is dead: reuse it for the partials
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm[j * kTrThreads + threadIdx.x] = csum[j];
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const float* p = sm + (c & 7) * kTrThreads + (c >> 3);
+            float t = 0.f;
+            for (int l = 0; l < vpb; ++l) t += p[l * C8];
+            atomicAdd(cs + (int64_t)n * cs_ld + c, t);
+        }
+    }
+}
+
+// out_sample[n][c] += part[n][c]; out_total[c] += sum_n part[n][c]: hands the column sums gn_bwd_apply_kernel<.., true>
+// left in a scratch buffer to their two destinations (timestep-embedding gradient per sample, conv bias gradient)
+__global__ void __launch_bounds__(256) colsum_scatter_kernel(const float* __restrict__ part, int64_t p_ld,
+                                                             float* __restrict__ out_sample, int64_t os_ld,
+                                                             float* __restrict__ out_total, int N, int C) {
+    pdl_prologue();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float t = 0.f;
+    for (int n = 0; n < N; ++n) {
+        const float v = part[(int64_t)n * p_ld + c];
+        if (out_sample != nullptr) out_sample[(int64_t)n * os_ld + c] += v;
+        t += v;
+    }
+    if (out_total != nullptr) out_total[c] += t;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -558,7 +600,17 @@ extern "C" int fcwdm_groupnorm_bwd(const void* x, int64_t x_ld, const void* dy, 
                                    const float* gamma, const float* beta, double* sums, const void* acc, int64_t acc_ld,
                                    void* dx, int64_t dx_ld, float* dgamma, float* dbeta, int64_t N, int64_t S, int64_t C,
                                    int64_t G, float eps, int silu, void* stream) {
+    return fcwdm_groupnorm_bwd_colsum(x, x_ld, dy, dy_ld, stats, gamma, beta, sums, acc, acc_ld, dx, dx_ld, dgamma, dbeta,
+                                      nullptr, 0, N, S, C, G, eps, silu, stream);
+}
+
+extern "C" int fcwdm_groupnorm_bwd_colsum(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, const double* stats,
+                                          const float* gamma, const float* beta, double* sums, const void* acc,
+                                          int64_t acc_ld, void* dx, int64_t dx_ld, float* dgamma, float* dbeta,
+                                          float* colsum, int64_t colsum_ld, int64_t N, int64_t S, int64_t C, int64_t G,
+                                          float eps, int silu, void* stream) {
     FCWDM_REQUIRE(x && dy && stats && gamma && beta && sums && dx, FCWDM_ERR_INVALID, "fcwdm_groupnorm_bwd: null pointer");
+    FCWDM_REQUIRE(colsum == nullptr || colsum_ld >= C, FCWDM_ERR_INVALID, "fcwdm_groupnorm_bwd: bad column-sum stride");
     int rc = gn_bwd_check("fcwdm_groupnorm_bwd", N, S, C, G);
     if (rc) return rc;
     FCWDM_REQUIRE(x_ld >= C && dy_ld >= C && dx_ld >= C && x_ld % 8 == 0 && dy_ld % 8 == 0 && dx_ld % 8 == 0 &&
@@ -572,20 +624,38 @@ extern "C" int fcwdm_groupnorm_bwd(const void* x, int64_t x_ld, const void* dy, 
     FCWDM_REQUIRE(e == cudaSuccess, FCWDM_ERR_CUDA, "fcwdm_groupnorm_bwd: memset failed (%s)", cudaGetErrorString(e));
     const dim3 grid = slab_grid(N, S, C, 4, 2);
     const dim3 blk((unsigned)((kTrThreads / (C / 8)) * (C / 8)));      // 256, or e.g. 240 for C = 192 / 384
-    const size_t sm1 = (16 * kTrThreads + 4 * C) * sizeof(float), sm2 = 8 * C * sizeof(float);
+    const size_t sm1 = (16 * kTrThreads + 4 * C) * sizeof(float);
+    const size_t sm2 = (colsum != nullptr && 8 * C < 8 * kTrThreads ? 8 * kTrThreads : 8 * C) * sizeof(float);
     const __nv_bfloat16 *xp = (const __nv_bfloat16*)x, *dp = (const __nv_bfloat16*)dy, *ap = (const __nv_bfloat16*)acc;
-    if (silu) {
+    if (silu)
         launch_k(gn_bwd_reduce_kernel<true>, grid, blk, sm1, st, xp, x_ld, dp, dy_ld, stats, gamma, beta, sums,
                  S, (int)C, (int)G, eps);
-        launch_k(gn_bwd_apply_kernel<true>, grid, blk, sm2, st, xp, x_ld, dp, dy_ld, stats, gamma, beta,
-                 (const double*)sums, ap, acc_ld, (__nv_bfloat16*)dx, dx_ld, dgamma, dbeta, S, (int)C, (int)G, eps);
-    } else {
+    else
         launch_k(gn_bwd_reduce_kernel<false>, grid, blk, sm1, st, xp, x_ld, dp, dy_ld, stats, gamma, beta, sums,
                  S, (int)C, (int)G, eps);
-        launch_k(gn_bwd_apply_kernel<false>, grid, blk, sm2, st, xp, x_ld, dp, dy_ld, stats, gamma, beta,
-                 (const double*)sums, ap, acc_ld, (__nv_bfloat16*)dx, dx_ld, dgamma, dbeta, S, (int)C, (int)G, eps);
+#define FCWDM_GN_BWD_APPLY(SILU, CS)                                                                                    \
+    launch_k(gn_bwd_apply_kernel<SILU, CS>, grid, blk, sm2, st, xp, x_ld, dp, dy_ld, stats, gamma, beta,                \
+             (const double*)sums, ap, acc_ld, (__nv_bfloat16*)dx, dx_ld, dgamma, dbeta, colsum, colsum_ld, S, (int)C,   \
+             (int)G, eps)
+    if (silu) {
+        if (colsum != nullptr) FCWDM_GN_BWD_APPLY(true, true); else FCWDM_GN_BWD_APPLY(true, false);
+    } else {
+        if (colsum != nullptr) FCWDM_GN_BWD_APPLY(false, true); else FCWDM_GN_BWD_APPLY(false, false);
     }
+#undef FCWDM_GN_BWD_APPLY
     FCWDM_CHECK_LAUNCH("fcwdm_groupnorm_bwd");
+    return FCWDM_OK;
+}
+
+extern "C" int fcwdm_colsum_scatter(const float* part, int64_t part_ld, float* out_sample, int64_t os_ld, float* out_total,
+                                    int64_t N, int64_t C, void* stream) {
+    FCWDM_REQUIRE(part && (out_sample || out_total), FCWDM_ERR_INVALID, "fcwdm_colsum_scatter: null pointer");
+    FCWDM_REQUIRE(N >= 0 && C >= 0 && part_ld >= C && (out_sample == nullptr || os_ld >= C), FCWDM_ERR_INVALID,
+                  "fcwdm_colsum_scatter: bad dimension");
+    if (N * C == 0) return FCWDM_OK;
+    launch_k(colsum_scatter_kernel, dim3((unsigned)((C + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, part, part_ld,
+             out_sample, os_ld, out_total, (int)N, (int)C);
+    FCWDM_CHECK_LAUNCH("fcwdm_colsum_scatter");
     return FCWDM_OK;
 }
 

@@ -41,6 +41,13 @@ class GradSync:
         # FCWDM_DDP_OVERLAP=0: hold every bucket until finish() (one exchange after the backward instead of under it);
         # a measurement knob -- NCCL's CTAs compete with the persistent conv kernels for SMs while they overlap
         self.overlap = os.environ.get("FCWDM_DDP_OVERLAP", "1") != "0"
+        # FCWDM_DDP_GRAD_DTYPE=bf16: exchange the gradient as bf16 (half the bytes on the wire: the bucket is converted on the
+        # side stream, averaged, and converted back into the fp32 flat gradient -- torch DDP's bf16_compress_hook).  The
+        # gradients come out of bf16 activations (relative error ~1e-2 per tensor), so the extra 2^-9 rounding is below
+        # their own noise; fp32 (the default) keeps the sum exact.
+        self.wire_dtype = torch.bfloat16 if os.environ.get("FCWDM_DDP_GRAD_DTYPE", "fp32").lower() in ("bf16", "bfloat16") \
+            else flat.dtype
+        self._wire = {}              # bucket -> persistent wire buffer (bf16 mode)
 
     def begin(self):
         self._pending = [b[2] for b in self.buckets]
@@ -65,15 +72,24 @@ class GradSync:
         chunk = self.flat[lo:hi]
         avg = self.backend == "nccl"
         op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
+        wire = chunk
+        if self.wire_dtype != chunk.dtype:
+            wire = self._wire.get(b)
+            if wire is None or wire.numel() != chunk.numel():
+                wire = self._wire[b] = torch.empty(chunk.numel(), dtype=self.wire_dtype, device=chunk.device)
         if self.stream is not None:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.flat.device))
             self.stream.wait_event(ev)
             with torch.cuda.stream(self.stream):
-                w = dist.all_reduce(chunk, op=op, group=self.group, async_op=True)
+                if wire is not chunk:
+                    wire.copy_(chunk)
+                w = dist.all_reduce(wire, op=op, group=self.group, async_op=True)
         else:
-            w = dist.all_reduce(chunk, op=op, group=self.group, async_op=True)
-        self._works.append((w, chunk, avg))
+            if wire is not chunk:
+                wire.copy_(chunk)
+            w = dist.all_reduce(wire, op=op, group=self.group, async_op=True)
+        self._works.append((w, chunk, avg, wire))
         self.launched += 1
 
     def finish(self):
@@ -83,16 +99,20 @@ class GradSync:
                 if not self._sent[b]:                          # held back (overlap off) or never completed (unused params)
                     self._pending[b] = 0
                     self._launch(b)
-            for w, chunk, avg in self._works:
+
+            def settle(w, chunk, avg, wire):
+                w.wait()
+                if wire is not chunk:
+                    chunk.copy_(wire)
+                if not avg:
+                    chunk.mul_(1.0 / self.world)
+
+            for work in self._works:
                 if self.stream is not None:
                     with torch.cuda.stream(self.stream):
-                        w.wait()
-                        if not avg:
-                            chunk.mul_(1.0 / self.world)
+                        settle(*work)
                 else:
-                    w.wait()
-                    if not avg:
-                        chunk.mul_(1.0 / self.world)
+                    settle(*work)
             if self.stream is not None:
                 torch.cuda.current_stream(self.flat.device).wait_stream(self.stream)
         self._works = []

@@ -62,6 +62,9 @@ PROTOTYPES = {
     "fcwdm_conv3d_transpose_flip_weights": (_c_int, [_c_p, _c_p, _c_i64, _c_i64, _c_int, _c_p]),
     "fcwdm_groupnorm_bwd": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p,
                                      _c_p] + [_c_i64] * 4 + [_c_f, _c_int, _c_p]),
+    "fcwdm_groupnorm_bwd_colsum": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64,
+                                            _c_p, _c_p, _c_p, _c_i64] + [_c_i64] * 4 + [_c_f, _c_int, _c_p]),
+    "fcwdm_colsum_scatter": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_p]),
     "fcwdm_colsum_cl": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_i64, _c_p]),
     "fcwdm_dwt3d_cl_bwd": (_c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_p, _c_i64, _c_p, _c_i64] + [_c_i64] * 5
                            + [_c_f, _c_f, _c_p]),

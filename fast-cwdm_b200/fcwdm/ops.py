@@ -453,12 +453,22 @@ def conv3d_transpose_flip_weights(w):
     return wt
 
 
-def groupnorm_bwd(x, dy, stats, gamma, beta, dx, dgamma, dbeta, N, S, C, G, eps=1e-5, silu=True, acc=None):
+def groupnorm_bwd(x, dy, stats, gamma, beta, dx, dgamma, dbeta, N, S, C, G, eps=1e-5, silu=True, acc=None, colsum=None):
+    """colsum: optional zero-initialised (N, >= C) fp32 buffer that receives the per-sample column sums of dx (the bias /
+    timestep-embedding gradient of the conv that produced x) from the same pass."""
     sums = torch.empty((N, GN_STAT_REPLICAS, C, 2), dtype=torch.float64, device=x.device)
     with _on(x.device) as st:
-        native.call("fcwdm_groupnorm_bwd", _ptr(x), x.stride(0), _ptr(dy), dy.stride(0), _ptr(stats), _ptr(gamma),
+        native.call("fcwdm_groupnorm_bwd_colsum", _ptr(x), x.stride(0), _ptr(dy), dy.stride(0), _ptr(stats), _ptr(gamma),
                     _ptr(beta), _ptr(sums), _ptr(acc), acc.stride(0) if acc is not None else 0, _ptr(dx), dx.stride(0),
-                    _ptr(dgamma), _ptr(dbeta), N, S, C, G, float(eps), 1 if silu else 0, st)
+                    _ptr(dgamma), _ptr(dbeta), _ptr(colsum), colsum.stride(0) if colsum is not None else 0, N, S, C, G,
+                    float(eps), 1 if silu else 0, st)
+
+
+def colsum_scatter(part, N, C, out_sample=None, out_total=None):
+    """out_sample[n, c] += part[n, c]; out_total[c] += sum_n part[n, c] (part: the colsum buffer of groupnorm_bwd)."""
+    with _on(part.device) as st:
+        native.call("fcwdm_colsum_scatter", _ptr(part), part.stride(0), _ptr(out_sample),
+                    out_sample.stride(0) if out_sample is not None else 0, _ptr(out_total), N, C, st)
 
 
 def colsum_cl(x, N, S, C, out_sample=None, out_total=None):

@@ -33,6 +33,12 @@ class WavUNetTrainEngine(WavUNetEngine):
         self._grads = {}
         self._keep = []
         self._uses = {}
+        self._wants_cs = {}              # id(conv output) -> C_out: its gradient's column sums are wanted (bias / embedding)
+        self._cs = {}                    # id(dx) -> (column sums taken by the GroupNorm backward that wrote dx, dx)
+        self._cs_arena = None
+        self._cs_pos = 0
+        import os
+        self.fuse_colsum = os.environ.get("FCWDM_NO_FUSED_COLSUM", "0") != "1"
         self.grad_ready_hook = None      # callable(lo, hi): flat-gradient range [lo, hi) is final (fcwdm.ddp)
         self.grad_sync = None            # fcwdm.ddp.GradSync: bucketed all-reduce overlapped with the backward
 
@@ -77,6 +83,16 @@ class WavUNetTrainEngine(WavUNetEngine):
             ops.add_cl(cur, g, out, rows, C)
             self._grads[id(t)] = out
 
+    def _cs_slot(self, N, C, device):
+        """(N, C) zeroed fp32 slice of the per-backward column-sum arena (one memset per backward)."""
+        n = N * C
+        if self._cs_arena is None or self._cs_arena.device != device or self._cs_pos + n > self._cs_arena.numel():
+            self._cs_arena = torch.zeros(max(n, 1 << 17), dtype=torch.float32, device=device)
+            self._cs_pos = 0
+        out = self._cs_arena[self._cs_pos:self._cs_pos + n].view(N, C)
+        self._cs_pos += n
+        return out
+
     @staticmethod
     def _buf7(rows, c, device):
         """The 7 high-frequency bands (7, rows, ld); pad channels (C < ld) must be zero: they meet zero weights in a conv."""
@@ -97,6 +113,8 @@ class WavUNetTrainEngine(WavUNetEngine):
         self._keep.append((x, y, residual))
         self._count(mod.weight, mod.bias)
         dims4 = (N,) + tuple(dims)
+        if (emb is not None or mod.bias is not None) and pk.cout % 8 == 0:
+            self._wants_cs[id(y)] = pk.cout      # a GroupNorm backward that writes d(y) can sum its columns on the way
 
         def bwd():
             dy = self._take(y)
@@ -110,8 +128,12 @@ class WavUNetTrainEngine(WavUNetEngine):
             if emb is not None or db is not None:
                 if pk.cout % 8:
                     raise FcwdmError("conv3d backward: C_out must be a multiple of 8")
-                ops.colsum_cl(dy, N, rows // N, cs, out_sample=emb[0][:, emb[1]:emb[1] + emb[2]] if emb else None,
-                              out_total=db)
+                out_sample = emb[0][:, emb[1]:emb[1] + emb[2]] if emb else None
+                pre = self._cs.pop(id(dy), None)
+                if pre is not None and pre[1] is dy:         # dy is exactly what that GroupNorm backward stored
+                    ops.colsum_scatter(pre[0], N, pk.cout, out_sample=out_sample, out_total=db)
+                else:
+                    ops.colsum_cl(dy, N, rows // N, cs, out_sample=out_sample, out_total=db)
             ops.conv3d_wgrad(x, dy, self._gp(mod.weight), dims4, pk.cin, pk.cout, pk.k, accumulate=True)
             if need_dx:
                 pt = self._conv_t[id(mod)]
@@ -141,8 +163,14 @@ class WavUNetTrainEngine(WavUNetEngine):
             if dy is None:
                 return
             dx = self._buf(N * S, C, x.device)
+            cs = None
+            if self.fuse_colsum and self._wants_cs.get(id(x)) == C:
+                # x is a conv output whose bias / embedding gradient is the column sum of d(x): taken in this pass.  The
+                # conv's backward uses it only if it receives THIS tensor (no later fan-in was added to it)
+                cs = self._cs_slot(N, C, x.device)
+                self._cs[id(dx)] = (cs, dx)
             ops.groupnorm_bwd(x, dy, stats, gamma, beta, dx, self._gp(gn.weight), self._gp(gn.bias), N, S, C,
-                              gn.num_groups, gn.eps, silu, acc=self._partial(x))
+                              gn.num_groups, gn.eps, silu, acc=self._partial(x), colsum=cs)
             self._set(x, dx)
             self._param_done(gn.weight, gn.bias)
 
@@ -377,6 +405,7 @@ class WavUNetTrainEngine(WavUNetEngine):
             self.prepare_train(dev)
             self.flat_grad(dev)
             self._tape, self._grads, self._keep, self._uses = [], {}, [], {}
+            self._wants_cs = {}
             self._stats.clear()
             self._arena = torch.zeros(1 << 18, dtype=torch.float64, device=dev)
             self._arena_pos = 0
@@ -443,6 +472,9 @@ class WavUNetTrainEngine(WavUNetEngine):
         dev = dout.device
         with torch.cuda.device(dev):
             self._gflat.zero_()
+            self._cs, self._cs_pos = {}, 0
+            if self._cs_arena is not None:
+                self._cs_arena.zero_()
             if self.grad_ready_hook is not None:
                 self._uses_left = dict(self._uses)
             if self.grad_sync is not None:
@@ -455,6 +487,7 @@ class WavUNetTrainEngine(WavUNetEngine):
             if self.grad_sync is not None:
                 self.grad_sync.finish()
             self._tape, self._grads, self._keep, self._out_cl = [], {}, [], None
+            self._cs, self._wants_cs = {}, {}
             self._stats.clear()
         return self._gflat
 
@@ -588,6 +621,7 @@ class UNetTrainEngine(WavUNetTrainEngine):
             self.prepare_train(dev)
             self.flat_grad(dev)
             self._tape, self._grads, self._keep, self._uses, self._emb_map = [], {}, [], {}, {}
+            self._wants_cs = {}
             S = D * H * W
             x_cl = torch.zeros((N * S, _ld(C)), dtype=torch.bfloat16, device=dev)
             ops.planar_to_cl(x.detach().float(), x_cl, C)

@@ -284,6 +284,15 @@ int fcwdm_groupnorm_bwd(const void* x, int64_t x_ld, const void* dy, int64_t dy_
                         const float* gamma, const float* beta, double* sums, const void* acc, int64_t acc_ld, void* dx,
                         int64_t dx_ld, float* dgamma, float* dbeta, int64_t N, int64_t S, int64_t C, int64_t G, float eps,
                         int silu, void* stream);
+/* the same, and colsum[n*colsum_ld + c] += sum_v dx[n,v,c] over the values it stores (colsum may be NULL): the bias /
+ * timestep-embedding gradient of the conv that produced x without another pass over dx.  fcwdm_colsum_scatter then adds
+ * such a [N][C] partial into its destinations: out_sample[n*os_ld + c] += part[n][c], out_total[c] += sum_n part[n][c]. */
+int fcwdm_groupnorm_bwd_colsum(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, const double* stats,
+                               const float* gamma, const float* beta, double* sums, const void* acc, int64_t acc_ld,
+                               void* dx, int64_t dx_ld, float* dgamma, float* dbeta, float* colsum, int64_t colsum_ld,
+                               int64_t N, int64_t S, int64_t C, int64_t G, float eps, int silu, void* stream);
+int fcwdm_colsum_scatter(const float* part, int64_t part_ld, float* out_sample, int64_t os_ld, float* out_total, int64_t N,
+                         int64_t C, void* stream);
 /* column sums of a cl bf16 tensor (conv bias and timestep-embedding gradients): out_sample[n*os_ld + c] += sum_v,
  * out_total[c] += sum_{n,v}; either may be NULL. */
 int fcwdm_colsum_cl(const void* x, int64_t ld, float* out_sample, int64_t os_ld, float* out_total, int64_t N, int64_t S,

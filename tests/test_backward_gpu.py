@@ -128,9 +128,22 @@ def test_groupnorm_silu_bwd(shape, silu, with_acc):
     dxc = torch.empty_like(xc)
     dgamma = torch.full((C,), 0.25, device="cuda")
     dbeta = torch.full((C,), -0.5, device="cuda")
+    cs = torch.zeros((N, C + 8), device="cuda")              # fused column sums of the stored dx (bias / embedding gradients)
     ops.groupnorm_bwd(xc, dyc, stats, gamma, beta, dxc, dgamma, dbeta, N, S, C, G, 1e-5, silu,
-                      acc=to_cl(acc) if with_acc else None)
+                      acc=to_cl(acc) if with_acc else None, colsum=cs)
     torch.cuda.synchronize()
+    want_cs = dxc.float().view(N, S, -1)[:, :, :C].sum(1)
+    assert float((cs[:, :C] - want_cs).abs().max()) <= 1e-3 * float(want_cs.abs().max()) + 1e-3
+    assert float(cs[:, C:].abs().max()) == 0.0
+    per, tot = torch.ones((N, C + 4), device="cuda"), torch.full((C,), 2.0, device="cuda")
+    ops.colsum_scatter(cs, N, C, out_sample=per[:, 4:], out_total=tot)
+    assert float((per[:, 4:] - 1.0 - cs[:, :C]).abs().max()) <= 1e-5 * float(cs.abs().max()) + 1e-6
+    assert float((tot - 2.0 - cs[:, :C].sum(0)).abs().max()) <= 1e-5 * float(cs.abs().max()) + 1e-5
+    assert float((per[:, :4] - 1.0).abs().max()) == 0.0
+    dx_plain = torch.empty_like(xc)                          # the variant without column sums stores the same dx
+    ops.groupnorm_bwd(xc, dyc, stats, gamma, beta, dx_plain, torch.zeros_like(dgamma), torch.zeros_like(dbeta), N, S, C, G,
+                      1e-5, silu, acc=to_cl(acc) if with_acc else None)
+    assert torch.equal(dx_plain, dxc)
     xr = x.clone().requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     y = F.group_norm(xr, G, gr, br, 1e-5)

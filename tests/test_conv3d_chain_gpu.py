@@ -104,6 +104,7 @@ CHAINS = [
     (1, (5, 7, 7), (1024, 256, 256)),                    # input-pyramid conv at the bottleneck (16 channel blocks, no GroupNorm in)
     (2, (4, 9, 11), (64, 128, 128, 256)),                # two samples, ragged tiles, C_in = 64 (one channel block: split 1)
     (1, (10, 14, 14), (1024, 128)),                      # single-layer chain (no barrier)
+    (1, (5, 7, 7), (256, 512, 1024)),                    # 16 and 32 channels per group in the fused statistics
 ]
 
 

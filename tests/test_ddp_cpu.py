@@ -4,6 +4,8 @@ bucketing / readiness logic of fcwdm.ddp.GradSync is host code over a flat tenso
 import os
 import socket
 
+import pytest
+
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -32,13 +34,15 @@ def test_bucket_partition_covers_every_parameter_once():
         assert b[0] <= lo and hi <= b[1]
 
 
-def _worker(rank, world, port):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+def _worker(rank, world, port, wire="fp32"):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      FCWDM_DDP_GRAD_DTYPE=wire)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sizes = [5, 1000, 3, 64, 4096, 7, 7, 20000, 1]
     offs, total = _offsets(sizes)
     flat = torch.zeros(total)
     gs = GradSync(flat, offs, bucket_bytes=4096 * 4)
+    assert gs.wire_dtype == (torch.bfloat16 if wire == "bf16" else torch.float32)
     for step in range(2):                                  # two steps: begin() re-arms the buckets
         gs.begin()
         for i, (lo, hi) in enumerate(offs):
@@ -57,9 +61,12 @@ def _worker(rank, world, port):
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_gradient_mean():
+@pytest.mark.parametrize("wire", ["fp32", "bf16"])
+def test_two_rank_gloo_gradient_mean(wire):
+    """wire = bf16: the bucket crosses the wire as bf16 and is widened back into the fp32 flat gradient (the test's values
+    and their sums are small integers and halves, exact in bf16)."""
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(2, port), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, wire), nprocs=2, join=True)

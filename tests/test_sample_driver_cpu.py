@@ -116,3 +116,83 @@ def test_driver_bookkeeping():
     assert subject_of(p, "validation/") == "BraTS-GLI-00001-000"     # the reference's [:19] rule
     assert subject_of(p) == "BraTS-GLI-00001-000"
     assert subject_of("/x/caseA/caseA-t1n.nii.gz") == "caseA"
+
+
+# nifti_1_header as published in nifti1.h (field, byte offset, struct format) -- written out here, independently of
+# fcwdm.nifti, as the yardstick for the header bytes.  "parity unpinned" for this one row: nibabel is not installed in
+# this image, so the golden below is built from the format's published layout plus the values nibabel's
+# Nifti1Image(array, affine) + nib.save are documented to set (sform 'aligned' = 2, qform 'unknown' = 0 with the
+# quaternion / offsets / pixdim of the affine still filled in, scl_slope 1 / scl_inter 0 for a float image written
+# without scaling, vox_offset 352, four zero extension bytes, everything else zero).
+NIFTI1_LAYOUT = [
+    ("sizeof_hdr", 0, "i"), ("data_type", 4, "10s"), ("db_name", 14, "18s"), ("extents", 32, "i"),
+    ("session_error", 36, "h"), ("regular", 38, "c"), ("dim_info", 39, "B"), ("dim", 40, "8h"),
+    ("intent_p1", 56, "f"), ("intent_p2", 60, "f"), ("intent_p3", 64, "f"), ("intent_code", 68, "h"),
+    ("datatype", 70, "h"), ("bitpix", 72, "h"), ("slice_start", 74, "h"), ("pixdim", 76, "8f"),
+    ("vox_offset", 108, "f"), ("scl_slope", 112, "f"), ("scl_inter", 116, "f"), ("slice_end", 120, "h"),
+    ("slice_code", 122, "B"), ("xyzt_units", 123, "B"), ("cal_max", 124, "f"), ("cal_min", 128, "f"),
+    ("slice_duration", 132, "f"), ("toffset", 136, "f"), ("glmax", 140, "i"), ("glmin", 144, "i"),
+    ("descrip", 148, "80s"), ("aux_file", 228, "24s"), ("qform_code", 252, "h"), ("sform_code", 254, "h"),
+    ("quatern_b", 256, "f"), ("quatern_c", 260, "f"), ("quatern_d", 264, "f"), ("qoffset_x", 268, "f"),
+    ("qoffset_y", 272, "f"), ("qoffset_z", 276, "f"), ("srow_x", 280, "4f"), ("srow_y", 296, "4f"),
+    ("srow_z", 312, "4f"), ("intent_name", 328, "16s"), ("magic", 344, "4s"),
+]
+
+
+def _golden_header(shape, affine):
+    values = {name: (0,) * int(fmt[:-1] or 1) if fmt[-1] in "hfiB" else (b"",) for name, _, fmt in NIFTI1_LAYOUT}
+    values.update(sizeof_hdr=(348,), regular=(b"\0",), dim=(len(shape), *shape, *([1] * (7 - len(shape)))), datatype=(16,),
+                  bitpix=(32,), pixdim=(1.0, *np.sqrt((affine[:3, :3] ** 2).sum(0)), 1.0, 1.0, 1.0, 1.0), vox_offset=(352.0,),
+                  scl_slope=(1.0,), scl_inter=(0.0,), qform_code=(0,), sform_code=(2,),
+                  qoffset_x=(affine[0, 3],), qoffset_y=(affine[1, 3],), qoffset_z=(affine[2, 3],),
+                  srow_x=tuple(affine[0]), srow_y=tuple(affine[1]), srow_z=tuple(affine[2]), magic=(b"n+1\0",))
+    out = bytearray(352)
+    end = 0
+    for name, off, fmt in NIFTI1_LAYOUT:
+        assert off == end, name                                       # the table itself is gap-free, 348 bytes
+        struct.pack_into("<" + fmt, out, off, *values[name])
+        end = off + struct.calcsize("<" + fmt)
+    assert end == 348
+    return bytes(out)
+
+
+@pytest.mark.parametrize("affine", [np.eye(4), np.diag([1.0, 1.5, 2.0, 1.0]) + np.array([[0, 0, 0, 3.0], [0, 0, 0, -4.0],
+                                                                                          [0, 0, 0, 5.5], [0, 0, 0, 0]])])
+def test_nifti_header_bytes_against_the_published_layout(tmp_path, affine):
+    """What sample.py:141-145 asks nibabel for -- nib.save(nib.Nifti1Image(arr, np.eye(4)), 'x.nii.gz') -- byte for byte:
+    the 352 header bytes, then the voxels in Fortran order as little-endian float32."""
+    a = np.random.default_rng(3).random((4, 3, 2)).astype(np.float32)
+    golden = _golden_header(a.shape, affine) + a.tobytes(order="F")
+    assert nifti.encode(a, affine=affine, gz=False) == golden
+    path = tmp_path / "x.nii.gz"
+    nifti.write(path, a, affine=affine)
+    assert gzip.decompress(path.read_bytes()) == golden
+    # and the reader against the same table: every field where the published layout puts it
+    h = nifti.parse_header(golden)
+    fields = {name: struct.unpack_from("<" + fmt, golden, off) for name, off, fmt in NIFTI1_LAYOUT}
+    assert h.dim == fields["dim"] and (h.datatype, h.bitpix) == (fields["datatype"][0], fields["bitpix"][0])
+    assert h.pixdim == fields["pixdim"] and h.vox_offset == 352.0 and (h.scl_slope, h.scl_inter) == (1.0, 0.0)
+    assert (h.qform_code, h.sform_code) == (0, 2) and np.array_equal(h.affine, affine)
+
+
+def test_nifti_multi_member_gzip_reads_as_one_stream(tmp_path):
+    """Volumes above 4 MB are deflated as independent gzip members on a thread pool (RFC 1952 section 2.2: a gzip file is a
+    series of members); gzip.decompress / GzipFile -- what nibabel opens .nii.gz with -- and zlib read them as one stream."""
+    import zlib
+    a = np.random.default_rng(5).random((96, 96, 160)).astype(np.float32)          # 5.9 MB -> two members
+    path = tmp_path / "big.nii.gz"
+    nifti.write(path, a)
+    blob = path.read_bytes()
+    plain = nifti.encode(a, gz=False)
+    assert gzip.decompress(blob) == plain
+    with gzip.GzipFile(path) as f:
+        assert f.read() == plain
+    members, rest = 0, blob
+    out = b""
+    while rest:
+        d = zlib.decompressobj(16 + zlib.MAX_WBITS)
+        out += d.decompress(rest)
+        rest = d.unused_data
+        members += 1
+    assert members == 2 and out == plain
+    assert np.array_equal(nifti.read(path, dtype=np.float32), a)
