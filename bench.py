@@ -573,8 +573,9 @@ def train_measure(device, world, rank, local, steps, warm, batch, want_roofline=
     slots = [slot, {k: torch.empty_like(v) for k, v in dev_batch.items()}]
     h2d_done = [torch.cuda.Event() for _ in range(2)]
     slot_free = [torch.cuda.Event() for _ in range(2)]
-    loss_cell = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-    loss_done = [torch.cuda.Event() for _ in range(2)]
+    LAG = 2                                       # the host reads step i's loss while steps i+1, i+2 are queued / running
+    loss_cell = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(LAG + 1)]
+    loss_done = [torch.cuda.Event() for _ in range(LAG + 1)]
     pipe = {"i": 0, "uploaded": -1}
 
     def upload(i):
@@ -596,13 +597,17 @@ def train_measure(device, world, rank, local, steps, warm, batch, want_roofline=
         upload(i + 1)                                                        # next step's batch, under this step's compute
         step(slots[s])
         slot_free[s].record(cur)
+        c = i % (LAG + 1)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(slot_free[s])
-            loss_cell[s].copy_(last["loss"], non_blocking=True)              # D2H of this step's result
-            loss_done[s].record(copy_stream)
-        if i > 0:
-            loss_done[1 - s].synchronize()
-            last["host_loss"] = float(loss_cell[1 - s])                      # the previous step's loss, on the host
+            loss_cell[c].copy_(last["loss"], non_blocking=True)              # D2H of this step's result
+            loss_done[c].record(copy_stream)
+        if i >= LAG:
+            # every step's loss reaches the host, LAG steps late: the launch queue keeps LAG steps of work while the host
+            # waits (one step of slack starved the GPU when two ranks share the host: 94 vs 113 samples/s at N = 2)
+            p = (i - LAG) % (LAG + 1)
+            loss_done[p].synchronize()
+            last["host_loss"] = float(loss_cell[p])
         pipe["i"] = i + 1
 
     def barrier():
@@ -637,8 +642,8 @@ def train_measure(device, world, rank, local, steps, warm, batch, want_roofline=
         ev.record(torch.cuda.current_stream(device))
     ms_e2e = timed(step_e2e, steps, 1)
     clk = clocks.stop()                           # covers the resident and the end-to-end timed regions
-    loss_done[(pipe["i"] - 1) % 2].synchronize()
-    last["host_loss"] = float(loss_cell[(pipe["i"] - 1) % 2])
+    loss_done[(pipe["i"] - 1) % (LAG + 1)].synchronize()
+    last["host_loss"] = float(loss_cell[(pipe["i"] - 1) % (LAG + 1)])
     finite = bool(torch.isfinite(last["loss"])) and last["host_loss"] == float(last["loss"])
     if rank != 0:
         return None

@@ -444,7 +444,11 @@ __global__ void __launch_bounds__(256) wgrad_finalize_small_kernel(const float* 
         float a = 0.f;
         if (cib + c < Cin) {
             const float* p = ws + ((size_t)tap * co_p + co) * ci_p + cib + c;
-            for (int sp = 0; sp < n_split; ++sp) a += p[sp * split_stride];
+            float v[8];                                   // n_split <= 8 here: all splits in flight at once, summed in order
+#pragma unroll
+            for (int sp = 0; sp < 8; ++sp) v[sp] = sp < n_split ? p[sp * split_stride] : 0.f;
+#pragma unroll
+            for (int sp = 0; sp < 8; ++sp) a += v[sp];
         }
         tile[tap][c] = a;
     }
