@@ -640,7 +640,7 @@ def train_measure(device, world, rank, local, steps, warm, batch, want_roofline=
     launches = native.launch_count - n0
     for ev in slot_free:
         ev.record(torch.cuda.current_stream(device))
-    ms_e2e = timed(step_e2e, steps, 1)
+    ms_e2e = timed(step_e2e, steps, max(1, warm))      # its own warm-up: the e2e slots change the allocator's steady state
     clk = clocks.stop()                           # covers the resident and the end-to-end timed regions
     loss_done[(pipe["i"] - 1) % (LAG + 1)].synchronize()
     last["host_loss"] = float(loss_cell[(pipe["i"] - 1) % (LAG + 1)])
