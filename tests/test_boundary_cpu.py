@@ -20,6 +20,10 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/fcwdm.h but not exported"
         assert name in native.PROTOTYPES, f"{name} has no ctypes prototype"
+    # INTEGRATION.md section 3 names the reference interface every entry point replaces: none may be missing there
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    undocumented = sorted(n for n in declared if f"`{n}`" not in doc)
+    assert not undocumented, f"entry points without a row in INTEGRATION.md: {undocumented}"
     assert lib.fcwdm_version() == 100
     assert lib.fcwdm_conv3d_packed_elems(64, 32, 3) == 27 * 64 * 64
     assert lib.fcwdm_conv3d_packed_elems(8, 64, 3) == 27 * 16 * 64
