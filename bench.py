@@ -573,7 +573,7 @@ def train_measure(device, world, rank, local, steps, warm, batch, want_roofline=
     slots = [slot, {k: torch.empty_like(v) for k, v in dev_batch.items()}]
     h2d_done = [torch.cuda.Event() for _ in range(2)]
     slot_free = [torch.cuda.Event() for _ in range(2)]
-    LAG = 2                                       # the host reads step i's loss while steps i+1, i+2 are queued / running
+    LAG = int(os.environ.get("FCWDM_BENCH_LAG", "2"))   # the host reads step i's loss while steps i+1 .. i+LAG are queued / running
     loss_cell = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(LAG + 1)]
     loss_done = [torch.cuda.Event() for _ in range(LAG + 1)]
     pipe = {"i": 0, "uploaded": -1}
@@ -621,16 +621,27 @@ def train_measure(device, world, rank, local, steps, warm, batch, want_roofline=
             fn()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = []
         e0.record()
         for _ in range(k):
             fn()
+            if os.environ.get("FCWDM_BENCH_STEP_TRACE") == "1":      # development: per-step device times on stderr
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record()
         e1.record()
         barrier()
+        if marks and rank == 0:
+            ts = [e0.elapsed_time(m) for m in marks]
+            print(fn.__name__, "per-step ms:", [round(b - a, 1) for a, b in zip([0.0] + ts[:-1], ts)], file=sys.stderr)
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    import gc
+    gc.collect()
+    gc.freeze()                                   # as guided_diffusion.train_util.TrainLoop.run_loop does (a generation-2
+    #                                               collection over the whole heap is a 32 ms host pause: one starved step)
     clocks = ClockSampler(local, enabled=(rank == 0))
     clocks.start()
     timed(step_resident, 0, warm)
@@ -640,7 +651,7 @@ def train_measure(device, world, rank, local, steps, warm, batch, want_roofline=
     launches = native.launch_count - n0
     for ev in slot_free:
         ev.record(torch.cuda.current_stream(device))
-    ms_e2e = timed(step_e2e, steps, max(1, warm))      # its own warm-up: the e2e slots change the allocator's steady state
+    ms_e2e = timed(step_e2e, steps, int(os.environ.get("FCWDM_BENCH_E2E_WARM", str(max(1, warm)))))   # its own warm-up
     clk = clocks.stop()                           # covers the resident and the end-to-end timed regions
     loss_done[(pipe["i"] - 1) % (LAG + 1)].synchronize()
     last["host_loss"] = float(loss_cell[(pipe["i"] - 1) % (LAG + 1)])

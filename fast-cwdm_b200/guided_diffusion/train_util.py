@@ -216,6 +216,13 @@ class TrainLoop:
         t_data = t_step = t_log = t_save = 0.0
         start = last = time.time()
         lossmse = None
+        # The host issues ~700 launches per step and stays about one step ahead of the GPU; a full (generation-2) Python
+        # garbage collection walks every object torch / numpy / the model tree ever created -- 32 ms here, a whole step --
+        # and the GPU drains meanwhile (measured: one 65 ms step in ~25, tools/train_stall_probe.py).  Everything alive now
+        # is long-lived, so it is moved out of the collector's reach; the per-step garbage (tape closures) stays collectable.
+        import gc
+        gc.collect()
+        gc.freeze()
         while not self.lr_anneal_steps or self.step + self.resume_step < self.lr_anneal_steps:
             now = time.time()
             t_total, last = now - last, now

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for v in "1 1" "2 1" "1 3" "2 3" "1 1"; do
+  set -- $v
+  FCWDM_BENCH_LAG=$1 FCWDM_BENCH_E2E_WARM=$2 timeout 600 python bench.py --workload train --batch 2 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_ab9.json 2> gpurun_out/r02_ab9.err
+  python -c "import json; d=json.load(open('gpurun_out/r02_ab9.json')); print('lag $1 warm $2:', round(d['value'],2), round(d['e2e']['value'],2))"
+done
