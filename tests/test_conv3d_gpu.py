@@ -99,7 +99,9 @@ def test_conv3d_full_resolution_shape():
 
 @pytest.mark.parametrize("case", [(2, 5, 18, 10, 64, 64, 3, 32), (1, 4, 16, 16, 128, 128, 3, 32),
                                   (1, 6, 10, 12, 64, 256, 1, 32), (2, 3, 7, 5, 32, 32, 3, 32),
-                                  (2, 5, 7, 7, 256, 256, 3, 32)])            # split-K: statistics from the leader only
+                                  (2, 5, 7, 7, 256, 256, 3, 32),             # split-K: statistics from the leader only
+                                  (1, 4, 16, 16, 64, 128, 3, 8), (1, 4, 16, 16, 64, 128, 3, 4),      # 16 / 32 / 64 channels per
+                                  (1, 4, 16, 16, 64, 128, 3, 2)])                                    # group: one reduce per 32 columns
 def test_conv3d_fused_groupnorm_statistics(case):
     """The epilogue's fused (sum, sumsq) per (n, group) of the stored bf16 output == statistics of that tensor."""
     from fcwdm import ops
